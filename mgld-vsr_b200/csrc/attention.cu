@@ -1,0 +1,303 @@
+// Fused softmax attention on tcgen05 (sm_100a):  O = softmax(scale * Q K^T) V, fp16 in / fp32 accumulate / fp16 out.
+//
+// One CTA = 128 query rows of one (batch, head).  Per 128-key block:
+//   warp 1 (one thread)  S = Q K_j^T        tcgen05.mma, SMEM x SMEM -> TMEM cols [0,128)
+//   warps 2-5 (128 thr)  one query row per thread (TMEM lane == row, so row max/sum need no shuffles):
+//                        online softmax, rescale of the O accumulator in TMEM, P_j (fp16) -> swizzled SMEM
+//   warp 1               O += P_j V_j        V consumed straight from its row-major [key, d] layout as an
+//                                            MN-major UMMA operand (no transpose anywhere)
+//   warp 0 (one thread)  TMA producer for Q once and a 2-stage K/V ring.
+// Two CTAs are resident per SM for head-dim 64 (112 KB smem, 256 TMEM columns each), so one CTA's softmax overlaps the
+// other's MMAs.
+//
+// Replaces xformers.ops.memory_efficient_attention at ldm/modules/attention.py:298 (self), :371 (cross, K/V
+// batch-broadcast as :336-337) and QKVAttentionLegacy at ldm/modules/diffusionmodules/openaimodel.py:554-590.
+#include <math.h>
+#include <string.h>
+
+#include "../../include/mgld.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mgld {
+
+constexpr int kQTile = 128;
+constexpr int kKVTile = 128;
+constexpr int kKVStages = 2;
+constexpr int kAttThreads = 192;
+
+struct AttnParams {
+  int nq, nkv, heads, batch;
+  int q_col0, k_col0, v_col0;        // column of head 0 in each matrix
+  int q_hstride, k_hstride, v_hstride;  // column stride between heads
+  int kv_batched;                    // 0: K/V shared by all batches (cross-attention context)
+  float scale_log2e;                 // scale * log2(e)
+  __half* out;
+  int ldo;                           // out row pitch (elements); out[(b*nq + i)*ldo + h*DH + d]
+};
+
+template <int DH>
+__global__ void __launch_bounds__(kAttThreads, DH == 64 ? 2 : 1)
+attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  constexpr int kHalves = DH / 64;                 // 64-column (128-byte) slabs per operand row
+  constexpr int kQBytes = kQTile * DH * 2;
+  constexpr int kKBytes = kKVTile * DH * 2;
+  constexpr int kSlab = kKVTile * 128;              // bytes of one [128 rows x 64 cols] swizzled slab
+  constexpr int kPBytes = kQTile * kKVTile * 2;
+  constexpr int kTmemCols = 256;
+  constexpr uint32_t kOCol = 128;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t q_full, kv_full[kKVStages], kv_empty[kKVStages], s_full, p_full, o_full;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sQ = smem_base;
+  const uint32_t sKV = sQ + kQBytes;                       // stage s: K at sKV + s*2*kKBytes, V right after K
+  const uint32_t sP = sKV + kKVStages * 2 * kKBytes;
+  uint8_t* sP_gen = smem_gen + (sP - smem_base);
+
+  const int q0 = blockIdx.x * kQTile;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int nblk = (p.nkv + kKVTile - 1) / kKVTile;
+  const int kvb = p.kv_batched ? b : 0;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(smem_u32(&q_full), 1);
+    for (int s = 0; s < kKVStages; ++s) { mbar_init(smem_u32(&kv_full[s]), 1); mbar_init(smem_u32(&kv_empty[s]), 1); }
+    mbar_init(smem_u32(&s_full), 1);
+    mbar_init(smem_u32(&p_full), 128);
+    mbar_init(smem_u32(&o_full), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      mbar_expect_tx(smem_u32(&q_full), kQBytes);
+#pragma unroll
+      for (int hf = 0; hf < kHalves; ++hf)
+        tma_load_3d(sQ + hf * kSlab, &tmQ, smem_u32(&q_full), p.q_col0 + head * p.q_hstride + hf * 64, q0, b);
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j % kKVStages;
+        const uint32_t ph = (j / kKVStages) & 1;
+        mbar_wait(smem_u32(&kv_empty[s]), ph ^ 1);
+        const uint32_t fb = smem_u32(&kv_full[s]);
+        mbar_expect_tx(fb, 2 * kKBytes);
+        const uint32_t sk = sKV + s * 2 * kKBytes, sv = sk + kKBytes;
+#pragma unroll
+        for (int hf = 0; hf < kHalves; ++hf) {
+          tma_load_3d(sk + hf * kSlab, &tmK, fb, p.k_col0 + head * p.k_hstride + hf * 64, j * kKVTile, kvb);
+          tma_load_3d(sv + hf * kSlab, &tmV, fb, p.v_col0 + head * p.v_hstride + hf * 64, j * kKVTile, kvb);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      const uint32_t idesc_s = umma_idesc_f16(kQTile, kKVTile, 0, 0);  // S[128 x 128] = Q (K-major) * K^T (K-major)
+      const uint32_t idesc_o = umma_idesc_f16(kQTile, DH, 0, 1);       // O[128 x DH] += P (K-major) * V (MN-major)
+      auto issue_s = [&](int j) {
+        const int s = j % kKVStages;
+        mbar_wait(smem_u32(&kv_full[s]), (j / kKVStages) & 1);
+        tc_fence_after();
+        const uint32_t sk = sKV + s * 2 * kKBytes;
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) {
+          const uint32_t off = (k >> 2) * kSlab + (k & 3) * 32;
+          umma_ss(tmem_base, umma_smem_desc(sQ + off, 0, 1024, kSwz128), umma_smem_desc(sk + off, 0, 1024, kSwz128),
+                  idesc_s, k != 0);
+        }
+        umma_commit(smem_u32(&s_full));
+      };
+      mbar_wait(smem_u32(&q_full), 0);
+      issue_s(0);
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j % kKVStages;
+        mbar_wait(smem_u32(&p_full), j & 1);
+        tc_fence_after();
+        const uint32_t sv = sKV + s * 2 * kKBytes + kKBytes;
+#pragma unroll
+        for (int k = 0; k < kKVTile / 16; ++k) {
+          // A: P rows are 2 slabs of 64 keys; B: V rows (keys) advance 16 * 128 B per step, LBO = next 64-col slab
+          const uint64_t adesc = umma_smem_desc(sP + (k >> 2) * kSlab + (k & 3) * 32, 0, 1024, kSwz128);
+          const uint64_t bdesc = umma_smem_desc(sv + k * 2048, kSlab, 1024, kSwz128);
+          umma_ss(tmem_base + kOCol, adesc, bdesc, idesc_o, (j | k) != 0);
+        }
+        umma_commit(smem_u32(&kv_empty[s]));
+        if (j + 1 < nblk) issue_s(j + 1);
+      }
+      umma_commit(smem_u32(&o_full));
+    }
+  } else {
+    // ---------------- softmax / correction / output (warps 2..5; thread == query row) ----------------
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(smem_u32(&s_full), j & 1);
+      tc_fence_after();
+      const int kv_left = p.nkv - j * kKVTile;  // keys valid in this block (>= 1)
+      // pass 1: row maximum of the raw scores
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c0 = 0; c0 < kKVTile; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(trow + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float v = (c0 + i < kv_left) ? __uint_as_float(r[i]) : -INFINITY;
+          mx = fmaxf(mx, v);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = exp2f((m_run - m_new) * p.scale_log2e);  // 0 on the first block (m_run = -inf)
+      const float mk = m_new * p.scale_log2e;
+      // pass 2: P = exp2(s*k - m*k) -> fp16 -> swizzled smem; row sum in fp32
+      float rs = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < kKVTile; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(trow + c0, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float e0 = (c0 + i < kv_left) ? exp2f(__uint_as_float(r[i]) * p.scale_log2e - mk) : 0.f;
+          float e1 = (c0 + i + 1 < kv_left) ? exp2f(__uint_as_float(r[i + 1]) * p.scale_log2e - mk) : 0.f;
+          const __half2 h2 = __floats2half2_rn(e0, e1);
+          // the row sum uses the fp16-rounded probabilities, i.e. exactly what multiplies V
+          const float2 back = __half22float2(h2);
+          rs += back.x + back.y;
+          pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
+        // 32 keys = 4 chunks of 16 bytes; slab = c0/64, chunk index inside the 128-byte row XOR (row & 7)
+        uint8_t* slab = sP_gen + (c0 >> 6) * kSlab + row * 128;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int chunk = (((c0 & 63) >> 3) + ch) ^ (row & 7);
+          *reinterpret_cast<uint4*>(slab + chunk * 16) = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+        }
+      }
+      // rescale O (written by PV_{j-1}, complete because s_full(j) was committed after it)
+      if (j > 0) {
+        const bool need = __any_sync(0xffffffffu, alpha != 1.f);
+        if (need) {
+#pragma unroll
+          for (int c0 = 0; c0 < DH; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_x32(trow + kOCol + c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st_x32(trow + kOCol + c0, r);
+          }
+          tmem_st_wait();
+        }
+      }
+      l_run = l_run * alpha + rs;
+      m_run = m_new;
+      fence_proxy_async_smem();   // P (generic-proxy stores) -> visible to the tensor core's async proxy
+      tc_fence_before();
+      mbar_arrive(smem_u32(&p_full));
+    }
+    // epilogue: O / l -> fp16 -> global
+    mbar_wait(smem_u32(&o_full), 0);
+    tc_fence_after();
+    const float inv = 1.f / l_run;
+    const int qi = q0 + row;
+    __half* orow = p.out + (static_cast<long long>(b) * p.nq + qi) * p.ldo + head * DH;
+#pragma unroll
+    for (int c0 = 0; c0 < DH; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_x32(trow + kOCol + c0, r);
+      tmem_ld_wait();
+      if (qi < p.nq) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 v;
+          v.x = pack_h2(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
+          v.y = pack_h2(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv);
+          v.z = pack_h2(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv);
+          v.w = pack_h2(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c0 + i) = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int DH>
+static int launch_attention(const mgld_attention_desc* d, cudaStream_t stream) {
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.nq = d->nq; p.nkv = d->nkv; p.heads = d->heads; p.batch = d->batch;
+  p.q_col0 = d->q_col0; p.k_col0 = d->k_col0; p.v_col0 = d->v_col0;
+  p.q_hstride = d->q_head_stride; p.k_hstride = d->k_head_stride; p.v_hstride = d->v_head_stride;
+  p.kv_batched = d->kv_batched;
+  p.scale_log2e = d->scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<__half*>(d->out); p.ldo = d->ldo;
+  CUtensorMap tmQ, tmK, tmV;
+  {
+    uint64_t dims[3] = {(uint64_t)d->ldq, (uint64_t)d->nq, (uint64_t)d->batch};
+    uint64_t str[2] = {(uint64_t)d->ldq * 2, (uint64_t)d->ldq * 2 * d->nq};
+    uint32_t box[3] = {64, kQTile, 1};
+    int rc = make_tmap_f16(&tmQ, d->q, 3, dims, str, box);
+    if (rc) return rc;
+    const int kvb = d->kv_batched ? d->batch : 1;
+    uint64_t dimsk[3] = {(uint64_t)d->ldk, (uint64_t)d->nkv, (uint64_t)kvb};
+    uint64_t strk[2] = {(uint64_t)d->ldk * 2, (uint64_t)d->ldk * 2 * d->nkv};
+    uint32_t boxk[3] = {64, kKVTile, 1};
+    rc = make_tmap_f16(&tmK, d->k, 3, dimsk, strk, boxk);
+    if (rc) return rc;
+    uint64_t dimsv[3] = {(uint64_t)d->ldv, (uint64_t)d->nkv, (uint64_t)kvb};
+    uint64_t strv[2] = {(uint64_t)d->ldv * 2, (uint64_t)d->ldv * 2 * d->nkv};
+    rc = make_tmap_f16(&tmV, d->v, 3, dimsv, strv, boxk);
+    if (rc) return rc;
+  }
+  const int smem = kQTile * DH * 2 + kKVStages * 2 * kKVTile * DH * 2 + kQTile * kKVTile * 2 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MGLD_CUDA(cudaFuncSetAttribute(attention_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(d->nq, kQTile), d->heads, d->batch);
+  attention_kernel<DH><<<grid, kAttThreads, smem, stream>>>(tmQ, tmK, tmV, p);
+  MGLD_LAUNCH_CHECK("attention_kernel");
+  return MGLD_OK;
+}
+
+}  // namespace mgld
+
+using namespace mgld;
+
+extern "C" int mgld_attention(const mgld_attention_desc* d, void* stream) {
+  if (!initialised()) { set_error("mgld_init() has not been called"); return MGLD_ERR_NOT_INIT; }
+  MGLD_CHECK_ARG(d && d->q && d->k && d->v && d->out, "attention: null pointer");
+  MGLD_CHECK_ARG(d->nq > 0 && d->nkv > 0 && d->heads > 0 && d->batch > 0, "attention: bad sizes");
+  MGLD_CHECK_ARG(d->head_dim == 64 || d->head_dim == 128, "attention: head_dim %d not supported (64, 128)",
+                 d->head_dim);
+  MGLD_CHECK_ARG(d->ldq % 8 == 0 && d->ldk % 8 == 0 && d->ldv % 8 == 0 && d->ldo % 8 == 0,
+                 "attention: row pitches must be multiples of 8 elements");
+  MGLD_CHECK_ARG(d->q_col0 % 8 == 0 && d->k_col0 % 8 == 0 && d->v_col0 % 8 == 0, "attention: column offsets");
+  if (d->head_dim == 64) return launch_attention<64>(d, (cudaStream_t)stream);
+  return launch_attention<128>(d, (cudaStream_t)stream);
+}

@@ -1,0 +1,56 @@
+// Host-side helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace mgld {
+
+enum : int {
+  MGLD_OK = 0,
+  MGLD_ERR_ARG = -1,      // invalid argument / unsupported shape
+  MGLD_ERR_CUDA = -2,     // a CUDA runtime / driver call failed
+  MGLD_ERR_NOT_INIT = -3  // mgld_init() not called
+};
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define MGLD_CHECK_ARG(cond, ...)     \
+  do {                                \
+    if (!(cond)) {                    \
+      ::mgld::set_error(__VA_ARGS__); \
+      return ::mgld::MGLD_ERR_ARG;    \
+    }                                 \
+  } while (0)
+
+#define MGLD_CUDA(call)                                                \
+  do {                                                                 \
+    cudaError_t e__ = (call);                                          \
+    if (e__ != cudaSuccess) return ::mgld::cuda_fail(e__, #call);      \
+  } while (0)
+
+#define MGLD_LAUNCH_CHECK(name)                                        \
+  do {                                                                 \
+    cudaError_t e__ = cudaGetLastError();                              \
+    if (e__ != cudaSuccess) return ::mgld::cuda_fail(e__, name);       \
+  } while (0)
+
+// cuTensorMapEncodeTiled obtained through cudaGetDriverEntryPoint (no link-time libcuda dependency).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn();
+int num_sms();
+bool initialised();
+
+// fp16 tensor map of rank `rank` (dims fastest-first, strides in BYTES for dims 1..rank-1), 128B swizzle unless
+// the inner box is narrower (64B -> SWIZZLE_64B, 32B -> SWIZZLE_32B).
+int make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, const uint32_t* elem_strides = nullptr);
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace mgld
