@@ -133,6 +133,56 @@ int mgld_canvas_posterior_f32(const float* x, const float* const* eps_tiles_dev,
                               const int* ofs_y, int tc, int h, int w, int tile_size, float c_recip, float c_recipm1,
                               float c1, float c2, float sigma, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Normalisation (fp16 NHWC activations, fp32 math)
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* GroupNorm statistics over the virtual concat [x1 | x2] (x2 may be NULL): sums[t][g] += (sum, sum of squares) in
+ * double; the caller zeroes `sums` ([T, groups, 2] doubles).  GroupNorm32 util.py:199-216 / Normalize model.py:80.     */
+int mgld_gn_stats_f16(const void* x1, int C1, int ld1, const void* x2, int C2, int ld2, int T, int HW, int groups,
+                      double* sums, void* stream);
+/* (sum, sumsq) -> fp32 (mean, rstd) pairs, for the SPADE epilogue of mgld_conv_gemm                                  */
+int mgld_gn_finalize(const double* sums, float* stats, int T, int groups, int HW, int C, double eps, void* stream);
+/* y = [silu]( (x - mean) * rstd * gamma + beta ), written as one dense [T*HW, C1+C2] tensor                           */
+int mgld_gn_apply_f16(const void* x1, int C1, int ld1, const void* x2, int C2, int ld2, int T, int HW, int groups,
+                      const double* sums, double eps, const float* gamma, const float* beta, int silu, void* out,
+                      int ldo, void* stream);
+/* nn.LayerNorm over the last dim (attention.py:132,423-425)                                                          */
+int mgld_layernorm_f16(const void* x, int ldx, int M, int C, const float* gamma, const float* beta, float eps,
+                       void* out, int ldo, void* stream);
+/* P = softmax(scale * S) row-wise, fp32 scores -> fp16 probabilities (VAE mid attention, model.py:294)               */
+int mgld_softmax_rows_f32(const float* s, long long lds, int rows, int n, float scale, void* p, long long ldp,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Layout / resampling / stems / small ops
+ * ------------------------------------------------------------------------------------------------------------------ */
+int mgld_nchw_f32_to_nhwc_f16(const float* in, void* out, int n, int c, int h, int w, int ldo, float scale, void* stream);
+int mgld_nhwc_f16_to_nchw_f32(const void* in, float* out, int n, int c, int h, int w, int ldi, float scale, void* stream);
+/* F.interpolate(scale_factor=2, mode="nearest"), NHWC fp16 (openaimodel.py:178-188, model.py:95-99)                   */
+int mgld_upsample_nearest2x_f16(const void* in, void* out, int t, int h, int w, int c, void* stream);
+/* im2col of a 3x3 stride-2 conv: pad=1 (openaimodel.py:204-231) or pad=0 with far-side zero fill (model.py:104-121)   */
+int mgld_im2col_s2_f16(const void* in, void* out, int t, int h, int w, int c, int ho, int wo, int pad, void* stream);
+/* direct conv, Cin <= 8: (N,Cin,H,W) fp32 -> NHWC fp16; w fp32 [Cout,Cin,ks,ks] (network stems)                        */
+int mgld_conv_small_cin_f32(const float* in, const float* w, const float* bias, void* out, int n, int cin, int h,
+                            int wd, int cout, int ks, int ldo, void* stream);
+/* direct conv fp32 NCHW -> NCHW, tiny channel counts (quant_conv / post_quant_conv, autoencoder.py:331-332)            */
+int mgld_conv_small_f32(const float* in, const float* w, const float* bias, float* out, int n, int cin, int h, int wd,
+                        int cout, int ks, void* stream);
+/* direct 3x3 conv, Cout in {2,3,4,8}: NHWC fp16 -> (N,Cout,H,W) fp32; w fp16 [Cout, 9*C] (network heads)               */
+int mgld_conv3x3_small_cout_f16(const void* in, const void* w, const float* bias, float* out, int n, int h, int wd,
+                                int c, int cout, int ldi, void* stream);
+/* y = [silu](W [silu](x) + bias + add): the M=1 linears of time_embed / emb_layers (openaimodel.py:2021-2025,418-424)  */
+int mgld_gemv_f32(const float* x, const void* w, const float* bias, const float* add, float* y, int n, int k,
+                  int silu_in, int silu_out, void* stream);
+/* timestep_embedding, util.py:151-171                                                                                 */
+int mgld_timestep_embedding_f32(float t, float* out, int dim, float max_period, void* stream);
+/* TemporalAttention core (attention.py:135-141): softmax over the T frames of each pixel; qkv fp16 [T,HW,3C]           */
+int mgld_temporal_attention_f16(const void* qkv, void* out, int t, int hw, int c, int heads, float scale, void* stream);
+/* DiagonalGaussianDistribution.sample * scale (distributions.py:24-37, ddpm.py:3382-3390)                              */
+int mgld_gaussian_sample_f32(const float* moments, const float* noise, float* out, int n, int cz, int h, int w,
+                             float scale, void* stream);
+int mgld_axpby_f16(const void* x, const void* y, void* out, float a, float b, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

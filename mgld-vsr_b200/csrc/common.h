@@ -1,6 +1,7 @@
 // Host-side helpers shared by the C-ABI translation units.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdint.h>

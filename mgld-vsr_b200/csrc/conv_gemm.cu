@@ -315,7 +315,9 @@ extern "C" int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream_) {
   if (!initialised()) { set_error("mgld_init() has not been called"); return MGLD_ERR_NOT_INIT; }
   MGLD_CHECK_ARG(d && d->a && d->w && d->out, "conv_gemm: null pointer");
   MGLD_CHECK_ARG(d->T > 0 && d->H > 0 && d->W > 0, "conv_gemm: bad T/H/W %d/%d/%d", d->T, d->H, d->W);
-  MGLD_CHECK_ARG(d->C1 > 0 && d->C1 % 64 == 0, "conv_gemm: C1=%d must be a positive multiple of 64", d->C1);
+  // K tail: with a single source and one tap the last 64-chunk may be partial (TMA zero-fills A and W alike)
+  MGLD_CHECK_ARG(d->C1 > 0 && (d->C1 % 64 == 0 || (d->C1 % 8 == 0 && d->taps == 1 && d->C2 == 0)),
+                 "conv_gemm: C1=%d must be a multiple of 64 (or of 8 for a single-source 1-tap GEMM)", d->C1);
   MGLD_CHECK_ARG(d->C2 >= 0 && d->C2 % 64 == 0 && ((d->C2 > 0) == (d->a2 != nullptr)),
                  "conv_gemm: C2=%d must be a multiple of 64 and match a2", d->C2);
   MGLD_CHECK_ARG(d->taps == 1 || d->taps == 3 || d->taps == 9, "conv_gemm: taps=%d", d->taps);
@@ -335,8 +337,8 @@ extern "C" int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream_) {
   p.tiles_w = ceil_div(d->W, p.BW);
   p.tiles_h = ceil_div(d->H, p.BH);
   p.tiles_t = ceil_div(d->T, p.BT);
-  p.kchunks1 = d->C1 / 64;
-  p.kchunks = (d->C1 + d->C2) / 64;
+  p.kchunks1 = ceil_div(d->C1, 64);
+  p.kchunks = ceil_div(d->C1 + d->C2, 64);
   p.taps = d->taps;
   p.N = d->N;
   p.block_n = pair ? 128 : (d->block_n > 0 ? d->block_n : pick_block_n(d->N));

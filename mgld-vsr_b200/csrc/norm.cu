@@ -1,0 +1,260 @@
+// Normalisation kernels (fp16 NHWC activations, fp32 math): GroupNorm statistics / apply(+SiLU), LayerNorm, and the
+// row softmax used by the unfused head-dim-512 VAE attention.  All HBM-bound: one read + one write of the activation,
+// 16-byte vector accesses, grids sized to cover the 148 SMs several times over.
+//
+// Replaces: GroupNorm32 (ldm/modules/diffusionmodules/util.py:199-216, eps 1e-5, fp32 math), Normalize
+// (ldm/modules/diffusionmodules/model.py:80, ldm/modules/attention.py:87, eps 1e-6), nn.SiLU / nonlinearity
+// (model.py:75-77), nn.LayerNorm (attention.py:132,423-425), the softmax inside memory_efficient_attention at
+// model.py:294.
+#include <math.h>
+
+#include "../../include/mgld.h"
+#include "common.h"
+
+namespace mgld {
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x; f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 v;
+  __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+
+// load 8 channels starting at channel c of row m from the (virtually concatenated) pair of sources
+__device__ __forceinline__ uint4 load_cat8(const __half* x1, int C1, int ld1, const __half* x2, int ld2, long long m,
+                                           int c) {
+  if (c < C1) return __ldg(reinterpret_cast<const uint4*>(x1 + m * ld1 + c));
+  return __ldg(reinterpret_cast<const uint4*>(x2 + m * ld2 + (c - C1)));
+}
+
+constexpr int kGnRowsPerBlock = 64;
+
+// sums[t][g] += (sum, sumsq) over rows [r0, r0+64) of frame t.  Double accumulation across blocks.
+__global__ void gn_stats_kernel(const __half* __restrict__ x1, int C1, int ld1, const __half* __restrict__ x2, int C2,
+                                int ld2, int HW, int G, double* __restrict__ sums) {
+  extern __shared__ float sh[];  // [2*G]
+  const int C = C1 + C2, vpr = C >> 3, cpg = C / G;
+  const int t = blockIdx.y;
+  const int r0 = blockIdx.x * kGnRowsPerBlock;
+  const int rows = min(kGnRowsPerBlock, HW - r0);
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  // thread -> fixed channel vector, strided rows: per-channel fp32 partials stay in registers
+  const int rpi = blockDim.x / vpr;  // rows handled per iteration (>= 1 because blockDim >= vpr)
+  const int v = threadIdx.x % vpr, rr = threadIdx.x / vpr;
+  if (rr < rpi) {
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+    for (int r = rr; r < rows; r += rpi) {
+      float f[8];
+      unpack8(load_cat8(x1, C1, ld1, x2, ld2, static_cast<long long>(t) * HW + r0 + r, v * 8), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+    }
+    // fold channels of the same group before touching shared memory
+    int g_prev = (v * 8) / cpg;
+    float as = 0.f, aq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (v * 8 + i) / cpg;
+      if (g != g_prev) { atomicAdd(&sh[2 * g_prev], as); atomicAdd(&sh[2 * g_prev + 1], aq); as = 0.f; aq = 0.f; g_prev = g; }
+      as += s[i]; aq += q[i];
+    }
+    atomicAdd(&sh[2 * g_prev], as); atomicAdd(&sh[2 * g_prev + 1], aq);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&sums[static_cast<long long>(t) * 2 * G + i], (double)sh[i]);
+}
+
+// (sum, sumsq) -> (mean, rstd) fp32
+__global__ void gn_finalize_kernel(const double* __restrict__ sums, float* __restrict__ stats, int n, double count,
+                                   double eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double mean = sums[2 * i] / count;
+  double var = sums[2 * i + 1] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[2 * i] = (float)mean;
+  stats[2 * i + 1] = (float)(1.0 / sqrt(var + eps));
+}
+
+// y = act( (x - mean) * rstd * gamma + beta )
+__global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, int ld1, const __half* __restrict__ x2, int C2,
+                                int ld2, int HW, int G, const double* __restrict__ sums, double eps,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                                __half* __restrict__ out, int ldo) {
+  extern __shared__ float sh[];  // [2*G] mean, rstd
+  const int C = C1 + C2, vpr = C >> 3, cpg = C / G;
+  const int t = blockIdx.y;
+  const double count = (double)HW * cpg;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    const double mean = sums[(static_cast<long long>(t) * G + g) * 2] / count;
+    double var = sums[(static_cast<long long>(t) * G + g) * 2 + 1] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    sh[2 * g] = (float)mean;
+    sh[2 * g + 1] = (float)(1.0 / sqrt(var + eps));
+  }
+  __syncthreads();
+  const int r0 = blockIdx.x * kGnRowsPerBlock;
+  const int rows = min(kGnRowsPerBlock, HW - r0);
+  for (int idx = threadIdx.x; idx < rows * vpr; idx += blockDim.x) {
+    const int r = idx / vpr, v = idx - r * vpr;
+    const long long m = static_cast<long long>(t) * HW + r0 + r;
+    float f[8];
+    unpack8(load_cat8(x1, C1, ld1, x2, ld2, m, v * 8), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = v * 8 + i, g = c / cpg;
+      float y = (f[i] - sh[2 * g]) * sh[2 * g + 1];
+      if (gamma) y = fmaf(y, __ldg(gamma + c), __ldg(beta + c));
+      if (silu) y = y / (1.f + __expf(-y));
+      f[i] = y;
+    }
+    *reinterpret_cast<uint4*>(out + m * ldo + v * 8) = pack8(f);
+  }
+}
+
+// LayerNorm over the last dim, one warp per row (C <= 2048, multiple of 8)
+constexpr int kLnMaxVec = 8;  // vectors of 8 per lane
+__global__ void layernorm_kernel(const __half* __restrict__ x, int ldx, int M, int C, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, __half* __restrict__ out, int ldo) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int vpr = C >> 3;
+  float f[kLnMaxVec][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kLnMaxVec; ++k) {
+    const int v = lane + 32 * k;
+    if (v < vpr) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + static_cast<long long>(warp) * ldx + v * 8)), f[k]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += f[k][i];
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < kLnMaxVec; ++k) {
+    if (lane + 32 * k < vpr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = f[k][i] - mean; q = fmaf(d, d, q); }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)C + eps);
+#pragma unroll
+  for (int k = 0; k < kLnMaxVec; ++k) {
+    const int v = lane + 32 * k;
+    if (v < vpr) {
+      float y[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = fmaf((f[k][i] - mean) * rstd, __ldg(gamma + v * 8 + i), __ldg(beta + v * 8 + i));
+      *reinterpret_cast<uint4*>(out + static_cast<long long>(warp) * ldo + v * 8) = pack8(y);
+    }
+  }
+}
+
+// P[r, :] = softmax(scale * S[r, :]) -> fp16; one block per row, fp32 scores (n up to ~16k)
+__global__ void softmax_rows_kernel(const float* __restrict__ s, long long lds, int n, float scale,
+                                    __half* __restrict__ p, long long ldp) {
+  __shared__ float red[32];
+  const float* row = s + blockIdx.x * lds;
+  __half* prow = p + blockIdx.x * ldp;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, row[i]);
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < (blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sum += __expf((row[i] - mx) * scale);
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) sum += red[i];
+  const float inv = 1.f / sum;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) prow[i] = __float2half_rn(__expf((row[i] - mx) * scale) * inv);
+}
+
+}  // namespace mgld
+
+using namespace mgld;
+
+static int gn_threads(int C) {
+  const int vpr = C / 8;
+  int th = 256;
+  while (th < vpr) th += 32;
+  return th;
+}
+
+extern "C" int mgld_gn_stats_f16(const void* x1, int C1, int ld1, const void* x2, int C2, int ld2, int T, int HW,
+                                 int groups, double* sums, void* stream) {
+  const int C = C1 + C2;
+  MGLD_CHECK_ARG(x1 && sums && T > 0 && HW > 0 && groups > 0, "gn_stats: bad arguments");
+  MGLD_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0 && C % groups == 0 && C / 8 <= 1024, "gn_stats: C1=%d C2=%d G=%d", C1, C2,
+                 groups);
+  MGLD_CHECK_ARG((C2 > 0) == (x2 != nullptr), "gn_stats: x2/C2 mismatch");
+  dim3 grid(ceil_div(HW, kGnRowsPerBlock), T);
+  gn_stats_kernel<<<grid, gn_threads(C), 2 * groups * sizeof(float), (cudaStream_t)stream>>>(
+      (const __half*)x1, C1, ld1 > 0 ? ld1 : C1, (const __half*)x2, C2, ld2 > 0 ? ld2 : C2, HW, groups, sums);
+  MGLD_LAUNCH_CHECK("gn_stats_kernel");
+  return MGLD_OK;
+}
+
+extern "C" int mgld_gn_finalize(const double* sums, float* stats, int T, int groups, int HW, int C, double eps,
+                                void* stream) {
+  MGLD_CHECK_ARG(sums && stats && T > 0 && groups > 0, "gn_finalize: bad arguments");
+  const int n = T * groups;
+  gn_finalize_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(sums, stats, n, (double)HW * (C / groups), eps);
+  MGLD_LAUNCH_CHECK("gn_finalize_kernel");
+  return MGLD_OK;
+}
+
+extern "C" int mgld_gn_apply_f16(const void* x1, int C1, int ld1, const void* x2, int C2, int ld2, int T, int HW,
+                                 int groups, const double* sums, double eps, const float* gamma, const float* beta,
+                                 int silu, void* out, int ldo, void* stream) {
+  const int C = C1 + C2;
+  MGLD_CHECK_ARG(x1 && sums && out && T > 0 && HW > 0 && groups > 0, "gn_apply: bad arguments");
+  MGLD_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0 && C % groups == 0, "gn_apply: C1=%d C2=%d G=%d", C1, C2, groups);
+  MGLD_CHECK_ARG((gamma != nullptr) == (beta != nullptr), "gn_apply: gamma/beta");
+  dim3 grid(ceil_div(HW, kGnRowsPerBlock), T);
+  gn_apply_kernel<<<grid, 256, 2 * groups * sizeof(float), (cudaStream_t)stream>>>(
+      (const __half*)x1, C1, ld1 > 0 ? ld1 : C1, (const __half*)x2, C2, ld2 > 0 ? ld2 : C2, HW, groups, sums, eps,
+      gamma, beta, silu, (__half*)out, ldo > 0 ? ldo : C);
+  MGLD_LAUNCH_CHECK("gn_apply_kernel");
+  return MGLD_OK;
+}
+
+extern "C" int mgld_layernorm_f16(const void* x, int ldx, int M, int C, const float* gamma, const float* beta,
+                                  float eps, void* out, int ldo, void* stream) {
+  MGLD_CHECK_ARG(x && out && gamma && beta && M > 0, "layernorm: bad arguments");
+  MGLD_CHECK_ARG(C % 8 == 0 && C / 8 <= 32 * kLnMaxVec, "layernorm: C=%d unsupported", C);
+  const int warps_per_block = 8;
+  layernorm_kernel<<<ceil_div(M, warps_per_block), warps_per_block * 32, 0, (cudaStream_t)stream>>>(
+      (const __half*)x, ldx > 0 ? ldx : C, M, C, gamma, beta, eps, (__half*)out, ldo > 0 ? ldo : C);
+  MGLD_LAUNCH_CHECK("layernorm_kernel");
+  return MGLD_OK;
+}
+
+extern "C" int mgld_softmax_rows_f32(const float* s, long long lds, int rows, int n, float scale, void* p,
+                                     long long ldp, void* stream) {
+  MGLD_CHECK_ARG(s && p && rows > 0 && n > 0, "softmax_rows: bad arguments");
+  softmax_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(s, lds, n, scale, (__half*)p, ldp);
+  MGLD_LAUNCH_CHECK("softmax_rows_kernel");
+  return MGLD_OK;
+}

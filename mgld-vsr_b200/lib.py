@@ -77,3 +77,17 @@ def stream_ptr():
 
 def ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class AttentionDesc(ctypes.Structure):
+    """Mirror of ``struct mgld_attention_desc`` (include/mgld.h)."""
+    _fields_ = [
+        ("q", ctypes.c_void_p), ("k", ctypes.c_void_p), ("v", ctypes.c_void_p),
+        ("ldq", ctypes.c_int32), ("ldk", ctypes.c_int32), ("ldv", ctypes.c_int32),
+        ("q_col0", ctypes.c_int32), ("k_col0", ctypes.c_int32), ("v_col0", ctypes.c_int32),
+        ("q_head_stride", ctypes.c_int32), ("k_head_stride", ctypes.c_int32), ("v_head_stride", ctypes.c_int32),
+        ("batch", ctypes.c_int32), ("heads", ctypes.c_int32), ("head_dim", ctypes.c_int32),
+        ("nq", ctypes.c_int32), ("nkv", ctypes.c_int32), ("kv_batched", ctypes.c_int32),
+        ("scale", ctypes.c_float),
+        ("out", ctypes.c_void_p), ("ldo", ctypes.c_int32),
+    ]

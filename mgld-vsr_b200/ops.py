@@ -89,3 +89,86 @@ def conv_gemm(a, w, *, taps=TAPS_1, a2=None, bias=None, epilogue=EPI_LINEAR, act
     d.out, d.ldout, d.out_col0, d.out_f32 = out.data_ptr(), ldout, out_col0, int(out_f32)
     _L.check(_L.lib().mgld_conv_gemm(ctypes.byref(d), _L.stream_ptr()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def attention(q, k, v, *, batch, heads, head_dim, nq, nkv, scale, q_col0=0, k_col0=0, v_col0=0,
+              q_head_stride=None, k_head_stride=None, v_head_stride=None, kv_batched=True, out=None):
+    """Fused softmax attention (mgld_attention).  q/k/v: fp16 2-D matrices [batch*n, ld] (may be the same buffer);
+    head h lives at columns [col0 + h*head_stride, +head_dim).  Returns out [batch*nq, heads*head_dim] fp16."""
+    for t in (q, k, v):
+        assert t.dtype == torch.float16 and t.is_cuda and t.dim() == 2 and t.stride(1) == 1
+    assert q.shape[0] >= batch * nq and k.shape[0] >= (batch if kv_batched else 1) * nkv
+    if out is None:
+        out = torch.empty(batch * nq, heads * head_dim, device=q.device, dtype=torch.float16)
+    d = _L.AttentionDesc()
+    d.q, d.k, d.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    d.ldq, d.ldk, d.ldv = q.stride(0), k.stride(0), v.stride(0)
+    d.q_col0, d.k_col0, d.v_col0 = q_col0, k_col0, v_col0
+    d.q_head_stride = head_dim if q_head_stride is None else q_head_stride
+    d.k_head_stride = head_dim if k_head_stride is None else k_head_stride
+    d.v_head_stride = head_dim if v_head_stride is None else v_head_stride
+    d.batch, d.heads, d.head_dim, d.nq, d.nkv = batch, heads, head_dim, nq, nkv
+    d.kv_batched, d.scale = int(kv_batched), float(scale)
+    d.out, d.ldo = out.data_ptr(), out.stride(0)
+    _L.check(_L.lib().mgld_attention(ctypes.byref(d), _L.stream_ptr()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# flow ops (fp32 NCHW)
+# ---------------------------------------------------------------------------------------------------------------
+def _f32c(t):
+    assert t.is_cuda and t.dtype == torch.float32
+    return t.contiguous()
+
+
+def flow_warp_f32(x, flow, flow_layout=0, nearest=False, border=False, align_corners=True):
+    x, flow = _f32c(x), _f32c(flow)
+    n, c, h, w = x.shape
+    out = torch.empty_like(x)
+    _L.check(_L.lib().mgld_flow_warp_f32(_L.ptr(x), _L.ptr(flow), _L.ptr(out), n, c, h, w, int(flow_layout),
+                                         int(nearest), int(border), int(align_corners), _L.stream_ptr()))
+    return out
+
+
+def flow_warp_bwd_input_f32(grad_out, flow, flow_layout=0, border=False, align_corners=True):
+    grad_out, flow = _f32c(grad_out), _f32c(flow)
+    n, c, h, w = grad_out.shape
+    gin = torch.empty_like(grad_out)
+    _L.check(_L.lib().mgld_flow_warp_bwd_input_f32(_L.ptr(grad_out), _L.ptr(flow), _L.ptr(gin), n, c, h, w,
+                                                   int(flow_layout), int(border), int(align_corners),
+                                                   _L.stream_ptr()))
+    return gin
+
+
+def fb_consistency_f32(fwd_flow, bwd_flow, alpha=0.01, beta=0.5):
+    fwd_flow, bwd_flow = _f32c(fwd_flow), _f32c(bwd_flow)
+    b, _, h, w = fwd_flow.shape
+    fo = torch.empty(b, h, w, device=fwd_flow.device, dtype=torch.float32)
+    bo = torch.empty_like(fo)
+    _L.check(_L.lib().mgld_fb_consistency_f32(_L.ptr(fwd_flow), _L.ptr(bwd_flow), _L.ptr(fo), _L.ptr(bo), b, h, w,
+                                              ctypes.c_float(alpha), ctypes.c_float(beta), _L.stream_ptr()))
+    return fo, bo
+
+
+def motion_guidance_f32(latents, flow_fwd_prop, flow_bwd_prop, fwd_occ, bwd_occ, step, want_loss=False):
+    """latents (t,c,h,w); flows (t-1,2,h,w); occs (t-1,h,w).  Returns latents - step * grad (and the loss)."""
+    latents = _f32c(latents)
+    t, c, h, w = latents.shape
+    ws = torch.empty_like(latents)
+    out = torch.empty_like(latents)
+    loss = torch.empty(1, device=latents.device, dtype=torch.float32) if want_loss else None
+    args = [_f32c(a) if a is not None else None for a in (flow_fwd_prop, flow_bwd_prop, fwd_occ, bwd_occ)]
+    _L.check(_L.lib().mgld_motion_guidance_f32(_L.ptr(latents), _L.ptr(args[0]), _L.ptr(args[1]), _L.ptr(args[2]),
+                                               _L.ptr(args[3]), _L.ptr(ws), _L.ptr(out), _L.ptr(loss),
+                                               ctypes.c_float(step), t, c, h, w, _L.stream_ptr()))
+    return (out, loss, ws) if want_loss else out
+
+
+def resize_flow_f32(flow, oh, ow):
+    flow = _f32c(flow)
+    n, _, h, w = flow.shape
+    out = torch.empty(n, 2, oh, ow, device=flow.device, dtype=torch.float32)
+    _L.check(_L.lib().mgld_resize_flow_f32(_L.ptr(flow), _L.ptr(out), n, h, w, oh, ow, _L.stream_ptr()))
+    return out

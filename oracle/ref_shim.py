@@ -126,6 +126,8 @@ def install():
 
     if REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
+    if os.path.join(REF_ROOT, "scripts") not in sys.path:   # the scripts import their siblings by bare name
+        sys.path.append(os.path.join(REF_ROOT, "scripts"))
 
     # oracle patch D1: infer t from b in the 4d<->5d / 4d<->3d helpers
     util = importlib.import_module("ldm.modules.diffusionmodules.util")
