@@ -127,8 +127,9 @@ int mgld_motion_guidance_f32(const float* latents, const float* flow_fwd_prop, c
 /* basicsr/archs/arch_util.py:235 resize_flow (bilinear, align_corners=False, values scaled by the size ratio)        */
 int mgld_resize_flow_f32(const float* flow, float* out, int n, int h, int w, int oh, int ow, void* stream);
 /* ddpm.py:4275-4316 + 4404-4417: Gaussian-weighted stitch of eps tiles, x0, posterior mean, noise add.
- * eps_tiles_dev: device array of n_tiles pointers to (tc, tile, tile) fp32 tiles; ofs_x/ofs_y: host arrays.          */
-int mgld_canvas_posterior_f32(const float* x, const float* const* eps_tiles_dev, const float* tile_w,
+ * eps_tiles_dev: device array of n_tiles pointers to (tc, tile, tile) fp32 tiles; tile_w: (tile, tile) fp64 weights
+ * (the reference keeps them in float64, ddpm.py:4610-4616); ofs_x/ofs_y: host arrays.                                */
+int mgld_canvas_posterior_f32(const float* x, const float* const* eps_tiles_dev, const double* tile_w,
                               const float* noise, float* out, float* eps_out, int n_tiles, const int* ofs_x,
                               const int* ofs_y, int tc, int h, int w, int tile_size, float c_recip, float c_recipm1,
                               float c1, float c2, float sigma, void* stream);
@@ -174,8 +175,8 @@ int mgld_conv3x3_small_cout_f16(const void* in, const void* w, const float* bias
 /* y = [silu](W [silu](x) + bias + add): the M=1 linears of time_embed / emb_layers (openaimodel.py:2021-2025,418-424)  */
 int mgld_gemv_f32(const float* x, const void* w, const float* bias, const float* add, float* y, int n, int k,
                   int silu_in, int silu_out, void* stream);
-/* timestep_embedding, util.py:151-171                                                                                 */
-int mgld_timestep_embedding_f32(float t, float* out, int dim, float max_period, void* stream);
+/* timestep_embedding, util.py:151-171; t is read from device memory (1 float) so the call is CUDA-graph replayable    */
+int mgld_timestep_embedding_f32(const float* t, float* out, int dim, float max_period, void* stream);
 /* TemporalAttention core (attention.py:135-141): softmax over the T frames of each pixel; qkv fp16 [T,HW,3C]           */
 int mgld_temporal_attention_f16(const void* qkv, void* out, int t, int hw, int c, int heads, float scale, void* stream);
 /* DiagonalGaussianDistribution.sample * scale (distributions.py:24-37, ddpm.py:3382-3390)                              */

@@ -221,7 +221,8 @@ __global__ void gemv_kernel(const float* __restrict__ x, const __half* __restric
 }
 
 // timestep_embedding (util.py:151-171): emb[i] = cos(t*f_i), emb[half+i] = sin(t*f_i), f_i = exp(-ln(max_period)*i/half)
-__global__ void timestep_embedding_kernel(float t, float* __restrict__ out, int dim, float max_period) {
+__global__ void timestep_embedding_kernel(const float* __restrict__ tp, float* __restrict__ out, int dim, float max_period) {
+  const float t = *tp;
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= half) return;
@@ -406,8 +407,8 @@ extern "C" int mgld_gemv_f32(const float* x, const void* w, const float* bias, c
   MGLD_LAUNCH_CHECK("gemv_kernel");
   return MGLD_OK;
 }
-extern "C" int mgld_timestep_embedding_f32(float t, float* out, int dim, float max_period, void* stream) {
-  MGLD_CHECK_ARG(out && dim > 0 && dim % 2 == 0, "timestep_embedding: bad arguments");
+extern "C" int mgld_timestep_embedding_f32(const float* t, float* out, int dim, float max_period, void* stream) {
+  MGLD_CHECK_ARG(t && out && dim > 0 && dim % 2 == 0, "timestep_embedding: bad arguments");
   timestep_embedding_kernel<<<ceil_div(dim / 2, 128), 128, 0, (cudaStream_t)stream>>>(t, out, dim, max_period);
   MGLD_LAUNCH_CHECK("timestep_embedding_kernel");
   return MGLD_OK;

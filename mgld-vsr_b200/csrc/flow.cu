@@ -257,7 +257,7 @@ struct TileList {
   int oy[64];
 };
 __global__ void canvas_posterior_kernel(const float* __restrict__ x, const float* const* __restrict__ eps_tiles,
-                                        const float* __restrict__ tile_w, const float* __restrict__ noise,
+                                        const double* __restrict__ tile_w, const float* __restrict__ noise,
                                         float* __restrict__ out, float* __restrict__ eps_out, TileList tl, int TC,
                                         int H, int W, int ts, float c_recip, float c_recipm1, float c1, float c2,
                                         float sigma) {
@@ -270,9 +270,11 @@ __global__ void canvas_posterior_kernel(const float* __restrict__ x, const float
   for (int i = 0; i < tl.n; ++i) {
     const int lx = px - tl.ox[i], ly = py - tl.oy[i];
     if (lx >= 0 && lx < ts && ly >= 0 && ly < ts) {
-      const float wgt = tile_w[ly * ts + lx];
-      acc = __fadd_rn(acc, __fmul_rn(eps_tiles[i][(tc * ts + ly) * ts + lx], wgt));
-      cnt = __fadd_rn(cnt, wgt);
+      // the reference accumulates fp32 += fp32 * fp64 weights (ddpm.py:4297-4298): type promotion makes each update
+      // a double-precision multiply-add rounded back to fp32
+      const double wgt = tile_w[ly * ts + lx];
+      acc = (float)((double)acc + (double)eps_tiles[i][(tc * ts + ly) * ts + lx] * wgt);
+      cnt = (float)((double)cnt + wgt);
     }
   }
   const float eps = __fdiv_rn(acc, cnt);
@@ -350,7 +352,7 @@ extern "C" int mgld_resize_flow_f32(const float* flow, float* out, int n, int h,
   return MGLD_OK;
 }
 
-extern "C" int mgld_canvas_posterior_f32(const float* x, const float* const* eps_tiles_dev, const float* tile_w,
+extern "C" int mgld_canvas_posterior_f32(const float* x, const float* const* eps_tiles_dev, const double* tile_w,
                                          const float* noise, float* out, float* eps_out, int n_tiles,
                                          const int* ofs_x, const int* ofs_y, int tc, int h, int w, int tile_size,
                                          float c_recip, float c_recipm1, float c1, float c2, float sigma,

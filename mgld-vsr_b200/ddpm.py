@@ -1,0 +1,485 @@
+"""LatentDiffusionVSRTextWT — the reference's sampling model class (ldm/models/diffusion/ddpm.py:3166), same
+constructor arguments (so the reference YAML instantiates it unchanged), same public methods / attributes the
+inference scripts use, on the mgld kernels.
+
+Hot loop structure (ddpm.py:4619-4694, 4383-4440, 4191-4322):
+  for i in reversed(range(S)):                      S respaced DDPM steps, strictly sequential
+      for each 64x64 latent tile:                   struct-cond encoder + UNet  -> eps tile   (one CUDA graph replay)
+      canvas_posterior kernel                       Gaussian-weighted eps stitch + x0 + posterior mean + noise add
+      motion_guidance kernel                        all 2(T-1) warps, masked L1 gradient, latent update
+Everything that only depends on (LR latent, t) or on the constant text context is hoisted (cross-attention K/V once
+per context tensor).
+"""
+import math
+from contextlib import contextmanager
+
+import numpy as np
+import torch
+
+from . import ops as _cuda_ops
+from .config import instantiate_from_config
+from .unet import _ModuleBase
+
+
+class FrozenOpenCLIPEmbedder(_ModuleBase):
+    """Stand-in for ldm/modules/encoders/modules.py:140.  The inference scripts only ever encode the empty prompt
+    ``['']`` (script :430-431), i.e. a constant (1,77,1024) tensor — out of scope as compute.
+    The embedding is supplied once (``set_embedding``), e.g. computed offline with open_clip."""
+
+    def __init__(self, arch="ViT-H-14", version="laion2b_s32b_b79k", device="cuda", max_length=77, freeze=True,
+                 layer="penultimate", **ignored):
+        self.device, self.max_length = device, max_length
+        self.embedding = None
+
+    def set_embedding(self, emb):
+        assert emb.dim() == 3 and emb.shape[0] == 1
+        self.embedding = emb
+
+    def load_state_dict(self, sd, strict=False, device="cuda"):
+        return [], list(sd)
+
+    def forward(self, text):
+        if list(text) != [""]:
+            raise NotImplementedError("only the empty prompt is used by the VSR inference path")
+        if self.embedding is None:
+            raise RuntimeError("FrozenOpenCLIPEmbedder: call set_embedding() with the (1,77,1024) empty-prompt embedding")
+        return self.embedding
+
+    __call__ = forward
+    encode = forward
+
+
+def make_beta_schedule(schedule, n_timestep, linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3):
+    """ldm/modules/diffusionmodules/util.py:21-43 (the schedules the configs use)"""
+    if schedule == "linear":
+        betas = torch.linspace(linear_start ** 0.5, linear_end ** 0.5, n_timestep, dtype=torch.float64) ** 2
+    elif schedule == "sqrt_linear":
+        betas = torch.linspace(linear_start, linear_end, n_timestep, dtype=torch.float64)
+    else:
+        raise ValueError(f"schedule '{schedule}' unknown.")
+    return betas.numpy()
+
+
+def space_timesteps(num_timesteps, section_counts):
+    """scripts/vsr_val_ddpm_text_T_vqganfin_oldcanvas_tile.py:33-88"""
+    if isinstance(section_counts, str):
+        if section_counts.startswith("ddim"):
+            desired = int(section_counts[len("ddim"):])
+            for i in range(1, num_timesteps):
+                if len(range(0, num_timesteps, i)) == desired:
+                    return set(range(0, num_timesteps, i))
+            raise ValueError(f"cannot create exactly {num_timesteps} steps with an integer stride")
+        section_counts = [int(x) for x in section_counts.split(",")]
+    size_per, extra = num_timesteps // len(section_counts), num_timesteps % len(section_counts)
+    start_idx, all_steps = 0, []
+    for i, section_count in enumerate(section_counts):
+        size = size_per + (1 if i < extra else 0)
+        if size < section_count:
+            raise ValueError(f"cannot divide section of {size} steps into {section_count}")
+        frac_stride = 1 if section_count <= 1 else (size - 1) / (section_count - 1)
+        cur_idx, taken = 0.0, []
+        for _ in range(section_count):
+            taken.append(start_idx + round(cur_idx))
+            cur_idx += frac_stride
+        all_steps += taken
+        start_idx += size
+    return set(all_steps)
+
+
+def extract_into_tensor(a, t, x_shape):
+    """util.py:96-99"""
+    b, *_ = t.shape
+    out = a.gather(-1, t)
+    return out.reshape(b, *((1,) * (len(x_shape) - 1)))
+
+
+class _EpsRunner:
+    """struct-cond encoder + UNet on one latent tile, captured in a CUDA graph per tile shape."""
+
+    def __init__(self, model, use_graph=True):
+        self.m, self.use_graph = model, use_graph
+        self.graphs = {}
+
+    def _eager(self, x, sc, t, context):
+        feats = self.m.structcond_stage_model(sc, t)
+        return self.m.model.diffusion_model(x, t, context=context, struct_cond=feats)
+
+    def __call__(self, x, sc, t, context):
+        if not (self.use_graph and x.is_cuda):
+            return self._eager(x, sc, t, context)
+        key = (tuple(x.shape), context.data_ptr(), context._version)
+        g = self.graphs.get(key)
+        if g is None:
+            sx, ssc, st = x.clone(), sc.clone(), t.clone()
+            self.m.model.diffusion_model.kvc.get(self.m.ops, context)   # K/V of the context computed outside the graph
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):                                       # warm-up (lazy init, allocator)
+                    self._eager(sx, ssc, st, context)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._eager(sx, ssc, st, context)
+            g = self.graphs[key] = (graph, sx, ssc, st, out)
+        graph, sx, ssc, st, out = g
+        sx.copy_(x); ssc.copy_(sc); st.copy_(t)
+        graph.replay()
+        return out.clone()
+
+
+class LatentDiffusionVSRTextWT(_ModuleBase):
+    def __init__(self, first_stage_config, cond_stage_config, structcond_stage_config, flownet_config=None,
+                 num_frames=1, num_timesteps_cond=None, cond_stage_key="image", cond_stage_trainable=False,
+                 concat_mode=True, cond_stage_forward=None, conditioning_key=None, scale_factor=1.0,
+                 scale_by_std=False, train_temporal_module=True, unfrozen_diff=False, random_size=False,
+                 test_gt=False, p2_gamma=None, p2_k=None, time_replace=None, use_usm=False, mix_ratio=0.0,
+                 unet_config=None, timesteps=1000, beta_schedule="linear", linear_start=1e-4, linear_end=2e-2,
+                 cosine_s=8e-3, given_betas=None, image_size=256, channels=3, log_every_t=100, parameterization="eps",
+                 v_posterior=0.0, ckpt_path=None, ignore_keys=(), ops=None, device="cuda", use_cuda_graph=True,
+                 **ignored):
+        assert parameterization == "eps", "the shipped config uses eps-parameterisation"
+        self.ops = ops or _cuda_ops
+        self.device = torch.device(device)
+        self.num_frames, self.scale_factor = num_frames, scale_factor
+        self.time_replace, self.image_size, self.channels = time_replace, image_size, channels
+        self.log_every_t, self.parameterization, self.v_posterior = log_every_t, parameterization, v_posterior
+        self.clip_denoised = False                                   # ddpm.py:3229
+        self.conditioning_key = conditioning_key or ("concat" if concat_mode else "crossattn")
+        self.configs = None                                          # the script sets model.configs = config (:301)
+        extra = {} if ops is None else {"ops": ops}
+        self.model = _DiffusionWrapper(instantiate_from_config(unet_config, **extra))
+        self.first_stage_model = instantiate_from_config(first_stage_config, **extra)
+        self.cond_stage_model = instantiate_from_config(cond_stage_config) if isinstance(cond_stage_config, dict) \
+            else None
+        self.structcond_stage_model = instantiate_from_config(structcond_stage_config, **extra)
+        self.flownet_model = instantiate_from_config(flownet_config, **extra) if flownet_config else None
+        self.register_schedule(given_betas=given_betas, beta_schedule=beta_schedule, timesteps=timesteps,
+                               linear_start=linear_start, linear_end=linear_end, cosine_s=cosine_s)
+        self.ori_timesteps = None
+        self._eps = _EpsRunner(self, use_graph=use_cuda_graph)
+
+    # ---- weights (script :91-108: torch.load(ckpt)["state_dict"], strict=False) ---------------------------------------
+    def load_state_dict(self, sd, strict=False):
+        def sub(prefix):
+            return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+        dev = str(self.device)
+        missing, unexpected = [], []
+        for prefix, mod in (("model.diffusion_model.", self.model.diffusion_model),
+                            ("first_stage_model.", self.first_stage_model),
+                            ("structcond_stage_model.", self.structcond_stage_model),
+                            ("flownet_model.", self.flownet_model)):
+            if mod is None:
+                continue
+            part = sub(prefix)
+            if not part and not strict:
+                missing.append(prefix + "*")
+                continue
+            m, u = mod.load_state_dict(part, strict=strict, device=dev)
+            missing += [prefix + k for k in m]
+            unexpected += [prefix + k for k in u]
+        return missing, unexpected
+
+    @contextmanager
+    def ema_scope(self, context=None):
+        yield None                                                    # use_ema: False in the shipped config (yaml:21)
+
+    # ---- schedule (ddpm.py:237-277) -----------------------------------------------------------------------------------
+    def register_schedule(self, given_betas=None, beta_schedule="linear", timesteps=1000, linear_start=1e-4,
+                          linear_end=2e-2, cosine_s=8e-3):
+        if given_betas is not None:
+            betas = np.asarray(given_betas, dtype=np.float64)
+        else:
+            betas = make_beta_schedule(beta_schedule, timesteps, linear_start, linear_end, cosine_s)
+        alphas = 1.0 - betas
+        ac = np.cumprod(alphas, axis=0)
+        ac_prev = np.append(1.0, ac[:-1])
+        (timesteps,) = betas.shape
+        self.num_timesteps = int(timesteps)
+        self.linear_start, self.linear_end = linear_start, linear_end
+        f32 = lambda a: torch.tensor(a, dtype=torch.float32, device=self.device)
+        post_var = (1 - self.v_posterior) * betas * (1.0 - ac_prev) / (1.0 - ac) + self.v_posterior * betas
+        self.betas, self.alphas_cumprod, self.alphas_cumprod_prev = f32(betas), f32(ac), f32(ac_prev)
+        self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod = f32(np.sqrt(ac)), f32(np.sqrt(1.0 - ac))
+        self.log_one_minus_alphas_cumprod = f32(np.log(1.0 - ac))
+        self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod = f32(np.sqrt(1.0 / ac)), f32(np.sqrt(1.0 / ac - 1))
+        self.posterior_variance = f32(post_var)
+        self.posterior_log_variance_clipped = f32(np.log(np.maximum(post_var, 1e-20)))
+        self.posterior_mean_coef1 = f32(betas * np.sqrt(ac_prev) / (1.0 - ac))
+        self.posterior_mean_coef2 = f32((1.0 - ac_prev) * np.sqrt(alphas) / (1.0 - ac))
+        # host copies of the per-step scalars the fused posterior kernel takes as arguments
+        self._h = {k: getattr(self, k).detach().cpu().numpy() for k in
+                   ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
+                    "posterior_mean_coef2", "posterior_log_variance_clipped")}
+
+    def respace(self, ddpm_steps):
+        """The schedule surgery of the inference script (:308-328): returns the 1000-step (sqrt_ac, sqrt_1m_ac) tables
+        needed by q_sample_respace and switches this model to the `ddpm_steps`-step respaced schedule."""
+        self.register_schedule(given_betas=None, beta_schedule="linear", timesteps=1000,
+                               linear_start=self.linear_start, linear_end=self.linear_end)
+        sqrt_ac, sqrt_1m_ac = self.sqrt_alphas_cumprod.clone(), self.sqrt_one_minus_alphas_cumprod.clone()
+        use = space_timesteps(1000, [ddpm_steps])
+        last, new_betas = 1, []
+        for i, a in enumerate(self.alphas_cumprod.cpu()):
+            if i in use:
+                new_betas.append(1 - a / last)
+                last = a
+        new_betas = [b.data.cpu().numpy() for b in new_betas]
+        self.register_schedule(given_betas=np.array(new_betas), timesteps=len(new_betas))
+        self.num_timesteps = 1000
+        self.ori_timesteps = sorted(list(use))
+        return sqrt_ac, sqrt_1m_ac
+
+    def q_sample_respace(self, x_start, t, sqrt_alphas_cumprod, sqrt_one_minus_alphas_cumprod, noise=None):
+        """ddpm.py:403-406"""
+        noise = torch.randn_like(x_start) if noise is None else noise
+        return (extract_into_tensor(sqrt_alphas_cumprod.to(noise.device), t, x_start.shape) * x_start +
+                extract_into_tensor(sqrt_one_minus_alphas_cumprod.to(noise.device), t, x_start.shape) * noise)
+
+    # ---- first stage ---------------------------------------------------------------------------------------------------
+    def encode_first_stage(self, x):
+        """ddpm.py:3906"""
+        return self.first_stage_model.encode(x)
+
+    def get_first_stage_encoding(self, encoder_posterior):
+        """ddpm.py:3382-3390"""
+        from .autoencoder import DiagonalGaussianDistribution
+        if isinstance(encoder_posterior, DiagonalGaussianDistribution):
+            z = encoder_posterior.sample()
+        elif isinstance(encoder_posterior, torch.Tensor):
+            z = encoder_posterior
+        else:
+            raise NotImplementedError(f"encoder_posterior of type '{type(encoder_posterior)}' not yet implemented")
+        return self.scale_factor * z
+
+    def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):
+        """ddpm.py:3786 — image VAE decode (used by the reference for logging; the VSR output goes through
+        VideoAutoencoderKLResi.decode instead)."""
+        if not hasattr(self.first_stage_model, "decode"):
+            raise NotImplementedError("AutoencoderKL.decode is not on the VSR inference path")
+        return self.first_stage_model.decode(1.0 / self.scale_factor * z)
+
+    def get_learned_conditioning(self, c):
+        return self.cond_stage_model(c)
+
+    # ---- flow ------------------------------------------------------------------------------------------------------------
+    def compute_flow(self, lrs):
+        """ddpm.py:3404-3429: lrs (n,t,c,h,w) in [0,1] -> (flows_forward, flows_backward), each (n,t-1,2,h,w)."""
+        n, t, c, h, w = lrs.size()
+        lrs_1 = lrs[:, :-1].reshape(-1, c, h, w)
+        lrs_2 = lrs[:, 1:].reshape(-1, c, h, w)
+        flows_backward = self.flownet_model(lrs_1, lrs_2).view(n, t - 1, 2, h, w)
+        flows_forward = self.flownet_model(lrs_2, lrs_1).view(n, t - 1, 2, h, w)
+        return flows_forward, flows_backward
+
+    # ---- denoiser -----------------------------------------------------------------------------------------------------------
+    def apply_model(self, x_noisy, t, cond, struct_cond, return_ids=False):
+        """ddpm.py:3984-4103 (crossattn conditioning; struct_cond is the struct-encoder feature dict)."""
+        if isinstance(cond, dict):
+            context = torch.cat(cond["c_crossattn"], 1)
+        elif isinstance(cond, list):
+            context = torch.cat(cond, 1)
+        else:
+            context = cond
+        return self.model.diffusion_model(x_noisy, t, context=context, struct_cond=struct_cond)
+
+    def _gaussian_weights(self, tile_width, tile_height, nbatches):
+        """ddpm.py:4601-4616 (float64; x midpoint (w-1)/2 but y midpoint h/2 — reproduced as is)."""
+        var = 0.01
+        midpoint = (tile_width - 1) / 2
+        x_probs = [math.exp(-(x - midpoint) * (x - midpoint) / (tile_width * tile_width) / (2 * var)) /
+                   math.sqrt(2 * math.pi * var) for x in range(tile_width)]
+        midpoint = tile_height / 2
+        y_probs = [math.exp(-(y - midpoint) * (y - midpoint) / (tile_height * tile_height) / (2 * var)) /
+                   math.sqrt(2 * math.pi * var) for y in range(tile_height)]
+        weights = np.outer(y_probs, x_probs)
+        ch = self.channels if self.configs is None else self.configs.model.params.channels
+        return torch.tile(torch.tensor(weights, device=self.device), (nbatches, ch, 1, 1))
+
+    @staticmethod
+    def _tile_offsets(h, w, tile_size, tile_overlap):
+        """tile grid of p_mean_variance_canvas (ddpm.py:4203-4231); "rows" run along x — reproduced as is."""
+        rows, cur = 0, 0
+        while cur < w:
+            cur = max(rows * tile_size - tile_overlap * rows, 0) + tile_size
+            rows += 1
+        cols, cur = 0, 0
+        while cur < h:
+            cur = max(cols * tile_size - tile_overlap * cols, 0) + tile_size
+            cols += 1
+        out = []
+        for row in range(rows):
+            for col in range(cols):
+                ofs_x = max(row * tile_size - tile_overlap * row, 0)
+                ofs_y = max(col * tile_size - tile_overlap * col, 0)
+                if row == rows - 1:
+                    ofs_x = w - tile_size
+                if col == cols - 1:
+                    ofs_y = h - tile_size
+                out.append((ofs_x, ofs_y))
+        return out
+
+    def _context(self, cond):
+        if isinstance(cond, dict):
+            return torch.cat(cond["c_crossattn"], 1)
+        if isinstance(cond, list):
+            return torch.cat(cond, 1)
+        return cond
+
+    def _posterior_step(self, x, eps_tiles, offsets, tile_size, tile_w, i, noise):
+        h = self._h
+        sigma = 0.0 if i == 0 else float(np.exp(np.float32(0.5) * h["posterior_log_variance_clipped"][i]))
+        return self.ops.canvas_posterior_f32(
+            x, eps_tiles, tile_w, noise, offsets, tile_size, float(h["sqrt_recip_alphas_cumprod"][i]),
+            float(h["sqrt_recipm1_alphas_cumprod"][i]), float(h["posterior_mean_coef1"][i]),
+            float(h["posterior_mean_coef2"][i]), sigma)
+
+    def _guidance(self, latents, flows, masks, guidance_scale, i):
+        """ddpm.py:4429-4435 with compute_temporal_condition_v4 (:3538): one fused kernel sequence."""
+        flow_fwd_prop, flow_bwd_prop = flows
+        fwd_occs, bwd_occs = masks
+        assert flow_fwd_prop.shape[0] == 1, "one clip per call (SURVEY.md D4)"
+        T = latents.shape[0]
+        step = float(guidance_scale) * float(self._h["posterior_log_variance_clipped"][i])
+        return self.ops.motion_guidance_f32(latents, flow_fwd_prop[0], flow_bwd_prop[0],
+                                            fwd_occs[0].reshape(T - 1, *latents.shape[-2:]),
+                                            bwd_occs[0].reshape(T - 1, *latents.shape[-2:]), step)
+
+    # ---- canvas sampler (ddpm.py:4383-4440, 4191-4322) -------------------------------------------------------------------
+    def p_sample_canvas(self, x, c, struct_cond, t, guidance_scale=-1.0, lr_images=None, flows=None, masks=None,
+                        clip_denoised=False, repeat_noise=False, return_codebook_ids=False, quantize_denoised=False,
+                        return_x0=False, temperature=1.0, noise_dropout=0.0, score_corrector=None,
+                        corrector_kwargs=None, t_replace=None, tile_size=64, tile_overlap=32, batch_size=4,
+                        tile_weights=None, _step=None):
+        assert tile_weights is not None
+        assert not (clip_denoised or quantize_denoised or return_codebook_ids or return_x0 or repeat_noise) \
+            and lr_images is None and score_corrector is None and noise_dropout == 0.0 and temperature == 1.0, \
+            "option not used by the VSR inference path"
+        i = int(t.reshape(-1)[0]) if _step is None else _step   # _step: host copy of t (avoids a device sync)
+        t_in = t if t_replace is None else t_replace
+        context = self._context(c)
+        _, _, h, w = x.shape
+        offsets = self._tile_offsets(h, w, tile_size, tile_overlap)
+        eps_tiles = []
+        for (ox, oy) in offsets:
+            xt = x[:, :, oy:oy + tile_size, ox:ox + tile_size].contiguous()
+            ct = struct_cond[:, :, oy:oy + tile_size, ox:ox + tile_size].contiguous()
+            eps_tiles.append(self._eps(xt, ct, t_in[:1], context))
+        noise = torch.randn(x.shape, device=x.device)                 # noise_like, util.py:265-268
+        latents = self._posterior_step(x, eps_tiles, offsets, tile_size, tile_weights[0, 0].contiguous(), i, noise)
+        if flows is not None:
+            latents = self._guidance(latents, flows, masks, guidance_scale, i)
+        return latents
+
+    def p_sample_loop_canvas(self, cond, struct_cond, shape, guidance_scale=-1.0, lr_images=None, flows=None,
+                             masks=None, return_intermediates=False, x_T=None, verbose=True, callback=None,
+                             timesteps=None, quantize_denoised=False, mask=None, x0=None, img_callback=None,
+                             start_T=None, log_every_t=None, time_replace=None, adain_fea=None, interfea_path=None,
+                             tile_size=64, tile_overlap=32, batch_size=4):
+        assert tile_size is not None
+        assert mask is None and adain_fea is None and interfea_path is None, "option not used by the VSR path"
+        log_every_t = log_every_t or self.log_every_t
+        device = self.device
+        b = shape[0] // self.num_frames
+        img = torch.randn(shape, device=device) if x_T is None else x_T
+        intermediates = [img]
+        timesteps = self.num_timesteps if timesteps is None else timesteps
+        if start_T is not None:
+            timesteps = min(timesteps, start_T)
+        tile_weights = self._gaussian_weights(tile_size, tile_size, 1)
+        for i in reversed(range(0, timesteps)):
+            ts = torch.full((b,), i, device=device, dtype=torch.long)
+            t_replace = None
+            if not (time_replace is None or time_replace == 1000):
+                t_replace = torch.full((batch_size,), self.ori_timesteps[i], device=device, dtype=torch.long)
+            img = self.p_sample_canvas(img, cond, struct_cond, ts, guidance_scale=guidance_scale, lr_images=lr_images,
+                                       flows=flows, masks=masks, clip_denoised=self.clip_denoised,
+                                       quantize_denoised=quantize_denoised, t_replace=t_replace, tile_size=tile_size,
+                                       tile_overlap=tile_overlap, batch_size=batch_size, tile_weights=tile_weights,
+                                       _step=i)
+            if i % log_every_t == 0 or i == timesteps - 1:
+                intermediates.append(img)
+            if callback:
+                callback(i)
+            if img_callback:
+                img_callback(img, i)
+        return (img, intermediates) if return_intermediates else img
+
+    @torch.no_grad()
+    def sample_canvas(self, cond, struct_cond, guidance_scale=-1.0, lr_images=None, flows=None, masks=None,
+                      batch_size=16, return_intermediates=False, x_T=None, verbose=True, timesteps=None,
+                      quantize_denoised=False, mask=None, x0=None, shape=None, time_replace=None, adain_fea=None,
+                      interfea_path=None, tile_size=64, tile_overlap=32, batch_size_sample=4, log_every_t=None,
+                      **kwargs):
+        """ddpm.py:4722-4760"""
+        if batch_size_sample != 1:
+            raise NotImplementedError("batch_size_sample > 1 mis-indexes tiles in the reference (SURVEY.md D5)")
+        if shape is None:
+            shape = (batch_size * self.num_frames, self.channels, self.image_size // 8, self.image_size // 8)
+        return self.p_sample_loop_canvas(cond, struct_cond, shape, guidance_scale=guidance_scale,
+                                         lr_images=lr_images, flows=flows, masks=masks,
+                                         return_intermediates=return_intermediates, x_T=x_T, verbose=verbose,
+                                         timesteps=timesteps, quantize_denoised=quantize_denoised, mask=mask, x0=x0,
+                                         time_replace=time_replace, adain_fea=adain_fea, interfea_path=interfea_path,
+                                         tile_size=tile_size, tile_overlap=tile_overlap, batch_size=batch_size_sample,
+                                         log_every_t=log_every_t)
+
+    # ---- untiled sampler (ddpm.py:4325-4381, 4501-4599, 4696-4720) ----------------------------------------------------
+    def p_sample_loop(self, cond, struct_cond, shape, guidance_scale=-1.0, lr_images=None, flows=None, masks=None,
+                      return_intermediates=False, x_T=None, verbose=True, callback=None, timesteps=None,
+                      quantize_denoised=False, mask=None, x0=None, img_callback=None, start_T=None, log_every_t=None,
+                      time_replace=None, adain_fea=None, interfea_path=None):
+        assert mask is None and adain_fea is None and interfea_path is None and lr_images is None, \
+            "option not used by the VSR path"
+        log_every_t = log_every_t or self.log_every_t
+        device = self.device
+        img = torch.randn(shape, device=device) if x_T is None else x_T
+        intermediates = [img]
+        timesteps = self.num_timesteps if timesteps is None else timesteps
+        context = self._context(cond)
+        _, _, h, w = img.shape
+        ones = torch.ones(h, w, device=device, dtype=torch.float64)
+        for i in reversed(range(0, timesteps)):
+            t_val = i if (time_replace is None or time_replace == 1000) else self.ori_timesteps[i]
+            if start_T is not None and t_val > start_T:
+                continue
+            t_in = torch.full((1,), t_val, device=device, dtype=torch.long)
+            eps = self._eps(img.contiguous(), struct_cond.contiguous(), t_in, context)
+            noise = torch.randn(img.shape, device=device)
+            # one full-frame "tile" with unit weight: the stitch degenerates to eps itself (exactly)
+            assert h == w, "the untiled path of the reference is used on square 512x512 crops"
+            img = self._posterior_step(img, [eps], [(0, 0)], h, ones, i, noise)
+            if flows is not None:
+                img = self._guidance(img, flows, masks, guidance_scale, i)
+            if i % log_every_t == 0 or i == timesteps - 1:
+                intermediates.append(img)
+            if callback:
+                callback(i)
+            if img_callback:
+                img_callback(img, i)
+        return (img, intermediates) if return_intermediates else img
+
+    @torch.no_grad()
+    def sample(self, cond, struct_cond, guidance_scale=-1.0, lr_images=None, flows=None, masks=None, batch_size=16,
+               return_intermediates=False, x_T=None, verbose=True, timesteps=None, quantize_denoised=False, mask=None,
+               x0=None, shape=None, time_replace=None, adain_fea=None, interfea_path=None, start_T=None, **kwargs):
+        """ddpm.py:4696-4720"""
+        if shape is None:
+            shape = (batch_size * self.num_frames, self.channels, self.image_size // 8, self.image_size // 8)
+        return self.p_sample_loop(cond, struct_cond, shape, guidance_scale=guidance_scale, lr_images=lr_images,
+                                  flows=flows, masks=masks, return_intermediates=return_intermediates, x_T=x_T,
+                                  verbose=verbose, timesteps=timesteps, quantize_denoised=quantize_denoised, mask=mask,
+                                  x0=x0, time_replace=time_replace, adain_fea=adain_fea, interfea_path=interfea_path,
+                                  start_T=start_T)
+
+
+class _DiffusionWrapper:
+    """ldm/models/diffusion/ddpm.py:4908-4963 (crossattn branch): keeps the `model.diffusion_model` attribute path."""
+
+    def __init__(self, diffusion_model):
+        self.diffusion_model = diffusion_model
+        self.conditioning_key = "crossattn"
+
+    def __call__(self, x, t, c_concat=None, c_crossattn=None, struct_cond=None, seg_cond=None):
+        cc = torch.cat(c_crossattn, 1)
+        return self.diffusion_model(x, t, context=cc, struct_cond=struct_cond)

@@ -172,3 +172,209 @@ def resize_flow_f32(flow, oh, ow):
     out = torch.empty(n, 2, oh, ow, device=flow.device, dtype=torch.float32)
     _L.check(_L.lib().mgld_resize_flow_f32(_L.ptr(flow), _L.ptr(out), n, h, w, oh, ow, _L.stream_ptr()))
     return out
+
+
+def canvas_posterior_f32(x, eps_tiles, tile_w, noise, offsets, tile_size, c_recip, c_recipm1, c1, c2, sigma,
+                         want_eps=False):
+    """Gaussian-weighted stitch of the eps tiles + x0 + posterior mean + noise add (mgld_canvas_posterior_f32).
+    x (T,C,h,w) fp32; eps_tiles: list of (T,C,ts,ts) fp32; tile_w (ts,ts) fp32; offsets [(ofs_x, ofs_y)]."""
+    x = _f32c(x)
+    T, C, h, w = x.shape
+    tiles = [_f32c(e) for e in eps_tiles]
+    ptrs = torch.tensor([e.data_ptr() for e in tiles], dtype=torch.int64).to(x.device, non_blocking=False)
+    n = len(tiles)
+    ox = (ctypes.c_int * n)(*[o[0] for o in offsets])
+    oy = (ctypes.c_int * n)(*[o[1] for o in offsets])
+    out = torch.empty_like(x)
+    eps_out = torch.empty_like(x) if want_eps else None
+    noise = _f32c(noise) if noise is not None else None
+    assert tile_w.dtype == torch.float64 and tile_w.is_cuda
+    tile_w = tile_w.contiguous()
+    _L.check(_L.lib().mgld_canvas_posterior_f32(
+        _L.ptr(x), _L.ptr(ptrs), _L.ptr(tile_w), _L.ptr(noise), _L.ptr(out), _L.ptr(eps_out), n, ox, oy, T * C, h, w,
+        tile_size, ctypes.c_float(c_recip), ctypes.c_float(c_recipm1), ctypes.c_float(c1), ctypes.c_float(c2),
+        ctypes.c_float(sigma), _L.stream_ptr()))
+    return (out, eps_out) if want_eps else out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# normalisation
+# ---------------------------------------------------------------------------------------------------------------
+def _thwc(x):
+    """(T, HW, C, row pitch) of an NHWC / [T, N, C] fp16 activation whose rows are uniformly strided."""
+    assert x.dtype == torch.float16 and x.is_cuda and x.stride(-1) == 1 and x.dim() >= 3
+    T, C, ld = x.shape[0], x.shape[-1], x.stride(-2)
+    HW = 1
+    for d in range(x.dim() - 2, 0, -1):
+        assert x.stride(d) == ld * HW, "rows must be uniformly strided"
+        HW *= x.shape[d]
+    assert x.stride(0) == ld * HW
+    return T, HW, C, ld
+
+
+def gn_stats(x1, x2=None, groups=32):
+    """-> double sums [T, groups, 2] over the virtual concat [x1 | x2] (NHWC fp16)."""
+    T, HW, C1, ld1 = _thwc(x1)
+    C2, ld2 = (x2.shape[-1], x2.stride(-2)) if x2 is not None else (0, 0)
+    sums = torch.zeros(T, groups, 2, device=x1.device, dtype=torch.float64)
+    _L.check(_L.lib().mgld_gn_stats_f16(_L.ptr(x1), C1, ld1, _L.ptr(x2), C2, ld2, T, HW, groups, _L.ptr(sums),
+                                        _L.stream_ptr()))
+    return sums
+
+
+def gn_finalize(sums, HW, C, eps):
+    T, G = sums.shape[:2]
+    stats = torch.empty(T, G, 2, device=sums.device, dtype=torch.float32)
+    _L.check(_L.lib().mgld_gn_finalize(_L.ptr(sums), _L.ptr(stats), T, G, HW, C, ctypes.c_double(eps), _L.stream_ptr()))
+    return stats
+
+
+def gn_apply(x1, sums, eps, gamma, beta, silu, x2=None, groups=32):
+    T, HW, C1, ld1 = _thwc(x1)
+    C2, ld2 = (x2.shape[-1], x2.stride(-2)) if x2 is not None else (0, 0)
+    out = torch.empty(*x1.shape[:-1], C1 + C2, device=x1.device, dtype=torch.float16)
+    _L.check(_L.lib().mgld_gn_apply_f16(_L.ptr(x1), C1, ld1, _L.ptr(x2), C2, ld2, T, HW, groups, _L.ptr(sums),
+                                        ctypes.c_double(eps), _L.ptr(gamma), _L.ptr(beta), int(silu), _L.ptr(out),
+                                        C1 + C2, _L.stream_ptr()))
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5):
+    assert x.dtype == torch.float16 and x.stride(-1) == 1
+    C = x.shape[-1]
+    M = x.numel() // C
+    assert x.is_contiguous()
+    out = torch.empty_like(x)
+    _L.check(_L.lib().mgld_layernorm_f16(_L.ptr(x), C, M, C, _L.ptr(gamma), _L.ptr(beta), ctypes.c_float(eps),
+                                         _L.ptr(out), C, _L.stream_ptr()))
+    return out
+
+
+def softmax_rows(s, scale, ldp=None):
+    """s fp32 [rows, n] -> fp16 [rows, ldp] (columns >= n are left as allocated: zero)."""
+    rows, n = s.shape
+    ldp = n if ldp is None else ldp
+    p = torch.zeros(rows, ldp, device=s.device, dtype=torch.float16) if ldp != n else \
+        torch.empty(rows, n, device=s.device, dtype=torch.float16)
+    _L.check(_L.lib().mgld_softmax_rows_f32(_L.ptr(s), ctypes.c_longlong(s.stride(0)), rows, n, ctypes.c_float(scale),
+                                            _L.ptr(p), ctypes.c_longlong(ldp), _L.stream_ptr()))
+    return p
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# layout / stems / small ops
+# ---------------------------------------------------------------------------------------------------------------
+def nchw_to_nhwc(x, scale=1.0):
+    x = _f32c(x)
+    n, c, h, w = x.shape
+    out = torch.empty(n, h, w, c, device=x.device, dtype=torch.float16)
+    _L.check(_L.lib().mgld_nchw_f32_to_nhwc_f16(_L.ptr(x), _L.ptr(out), n, c, h, w, c, ctypes.c_float(scale),
+                                                _L.stream_ptr()))
+    return out
+
+
+def nhwc_to_nchw(x, scale=1.0):
+    assert x.dtype == torch.float16 and x.is_contiguous()
+    n, h, w, c = x.shape
+    out = torch.empty(n, c, h, w, device=x.device, dtype=torch.float32)
+    _L.check(_L.lib().mgld_nhwc_f16_to_nchw_f32(_L.ptr(x), _L.ptr(out), n, c, h, w, c, ctypes.c_float(scale),
+                                                _L.stream_ptr()))
+    return out
+
+
+def upsample2x(x):
+    assert x.dtype == torch.float16 and x.is_contiguous()
+    t, h, w, c = x.shape
+    out = torch.empty(t, 2 * h, 2 * w, c, device=x.device, dtype=torch.float16)
+    _L.check(_L.lib().mgld_upsample_nearest2x_f16(_L.ptr(x), _L.ptr(out), t, h, w, c, _L.stream_ptr()))
+    return out
+
+
+def im2col_s2(x, pad):
+    """-> [T, Ho, Wo, 9*C] patches of a 3x3 stride-2 conv (pad=1 symmetric, pad=0 = F.pad(0,1,0,1))."""
+    assert x.dtype == torch.float16 and x.is_contiguous()
+    t, h, w, c = x.shape
+    ho = (h + 2 * pad - 3) // 2 + 1 if pad == 1 else (h + 1 - 3) // 2 + 1
+    wo = (w + 2 * pad - 3) // 2 + 1 if pad == 1 else (w + 1 - 3) // 2 + 1
+    out = torch.empty(t, ho, wo, 9 * c, device=x.device, dtype=torch.float16)
+    _L.check(_L.lib().mgld_im2col_s2_f16(_L.ptr(x), _L.ptr(out), t, h, w, c, ho, wo, pad, _L.stream_ptr()))
+    return out
+
+
+def conv_small_cin(x, w, bias):
+    """x (N,Cin<=8,H,W) fp32, w fp32 [Cout,Cin,ks,ks] -> NHWC fp16 [N,H,W,Cout]"""
+    x = _f32c(x)
+    n, cin, h, wd = x.shape
+    cout, _, ks, _ = w.shape
+    out = torch.empty(n, h, wd, cout, device=x.device, dtype=torch.float16)
+    _L.check(_L.lib().mgld_conv_small_cin_f32(_L.ptr(x), _L.ptr(w), _L.ptr(bias), _L.ptr(out), n, cin, h, wd, cout, ks,
+                                              cout, _L.stream_ptr()))
+    return out
+
+
+def conv_small_f32(x, w, bias):
+    x = _f32c(x)
+    n, cin, h, wd = x.shape
+    cout, _, ks, _ = w.shape
+    out = torch.empty(n, cout, h, wd, device=x.device, dtype=torch.float32)
+    _L.check(_L.lib().mgld_conv_small_f32(_L.ptr(x), _L.ptr(w), _L.ptr(bias), _L.ptr(out), n, cin, h, wd, cout, ks,
+                                          _L.stream_ptr()))
+    return out
+
+
+def conv3x3_small_cout(x, w_packed, bias):
+    """x NHWC fp16 [N,H,W,C], w_packed fp16 [Cout, 9*C] -> (N,Cout,H,W) fp32"""
+    assert x.dtype == torch.float16 and x.is_contiguous()
+    n, h, wd, c = x.shape
+    cout = w_packed.shape[0]
+    out = torch.empty(n, cout, h, wd, device=x.device, dtype=torch.float32)
+    _L.check(_L.lib().mgld_conv3x3_small_cout_f16(_L.ptr(x), _L.ptr(w_packed), _L.ptr(bias), _L.ptr(out), n, h, wd, c,
+                                                  cout, c, _L.stream_ptr()))
+    return out
+
+
+def gemv(x, w, bias=None, add=None, silu_in=False, silu_out=False):
+    """x fp32 [K], w fp16 [N,K] -> fp32 [N]"""
+    n, k = w.shape
+    y = torch.empty(n, device=w.device, dtype=torch.float32)
+    _L.check(_L.lib().mgld_gemv_f32(_L.ptr(x), _L.ptr(w), _L.ptr(bias), _L.ptr(add), _L.ptr(y), n, k, int(silu_in),
+                                    int(silu_out), _L.stream_ptr()))
+    return y
+
+
+def timestep_embedding(t, dim, max_period=10000.0):
+    """t: CUDA fp32 tensor with one element (read on the device, so the launch is graph-replayable)."""
+    assert t.is_cuda and t.dtype == torch.float32 and t.numel() == 1
+    out = torch.empty(dim, device=t.device, dtype=torch.float32)
+    _L.check(_L.lib().mgld_timestep_embedding_f32(_L.ptr(t), _L.ptr(out), dim,
+                                                  ctypes.c_float(max_period), _L.stream_ptr()))
+    return out
+
+
+def temporal_attention(qkv, heads, scale):
+    """qkv fp16 [T, HW, 3C] -> [T, HW, C]"""
+    assert qkv.dtype == torch.float16 and qkv.is_contiguous()
+    t, hw, c3 = qkv.shape
+    c = c3 // 3
+    out = torch.empty(t, hw, c, device=qkv.device, dtype=torch.float16)
+    _L.check(_L.lib().mgld_temporal_attention_f16(_L.ptr(qkv), _L.ptr(out), t, hw, c, heads, ctypes.c_float(scale),
+                                                  _L.stream_ptr()))
+    return out
+
+
+def gaussian_sample(moments, noise, scale):
+    moments = _f32c(moments)
+    n, c2, h, w = moments.shape
+    out = torch.empty(n, c2 // 2, h, w, device=moments.device, dtype=torch.float32)
+    noise = _f32c(noise) if noise is not None else None
+    _L.check(_L.lib().mgld_gaussian_sample_f32(_L.ptr(moments), _L.ptr(noise), _L.ptr(out), n, c2 // 2, h, w,
+                                               ctypes.c_float(scale), _L.stream_ptr()))
+    return out
+
+
+def axpby(x, y, a, b):
+    assert x.dtype == torch.float16 and x.is_contiguous() and y.is_contiguous() and x.shape == y.shape
+    out = torch.empty_like(x)
+    _L.check(_L.lib().mgld_axpby_f16(_L.ptr(x), _L.ptr(y), _L.ptr(out), ctypes.c_float(a), ctypes.c_float(b),
+                                     ctypes.c_longlong(x.numel()), _L.stream_ptr()))
+    return out

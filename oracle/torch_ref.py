@@ -595,7 +595,7 @@ class RefModel:
 
     def posterior(self, x, eps, i):
         """predict_start_from_noise ddpm.py:340-344 + q_posterior :346-353"""
-        s = self.sched
+        s = {k: v.to(x.device) for k, v in self.sched.items()}
         x0 = s["sqrt_recip_alphas_cumprod"][i] * x - s["sqrt_recipm1_alphas_cumprod"][i] * eps
         mean = s["posterior_mean_coef1"][i] * x0 + s["posterior_mean_coef2"][i] * x
         return mean, s["posterior_log_variance_clipped"][i]
@@ -603,10 +603,10 @@ class RefModel:
     def p_sample_canvas(self, x, context, struct_cond, i, noise, flows, masks, guidance_scale, tile_size, tile_overlap,
                         tile_weights):
         """p_sample_canvas ddpm.py:4383-4440 + p_mean_variance_canvas :4191-4322 (batch_size_sample = 1)."""
-        t_in = torch.full((1,), self.ori_timesteps[i], dtype=torch.long)
+        t_in = torch.full((1,), self.ori_timesteps[i], dtype=torch.long, device=x.device)
         _, _, h, w = x.shape
-        noise_pred = torch.zeros(x.shape)
-        contributors = torch.zeros(x.shape)
+        noise_pred = torch.zeros(x.shape, device=x.device)
+        contributors = torch.zeros(x.shape, device=x.device)
         for (ox, oy) in canvas_tiles(h, w, tile_size, tile_overlap):
             e = self.eps(x[:, :, oy:oy + tile_size, ox:ox + tile_size], t_in, context,
                          struct_cond[:, :, oy:oy + tile_size, ox:ox + tile_size])
@@ -624,7 +624,7 @@ class RefModel:
                       tile_size=64, tile_overlap=32, return_eps=False):
         """sample_canvas / p_sample_loop_canvas, ddpm.py:4722-4760, 4619-4694.  noises[i] = the randn drawn at step i."""
         S = len(self.ori_timesteps)
-        tw = gaussian_weights(tile_size, tile_size, 1)
+        tw = gaussian_weights(tile_size, tile_size, 1).to(x_T.device)
         img, eps_trace = x_T, []
         for i in reversed(range(S)):
             img, e = self.p_sample_canvas(img, context, struct_cond, i, noises[i], flows, masks, guidance_scale,

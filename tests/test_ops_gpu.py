@@ -1,0 +1,238 @@
+"""GPU parity of every C-ABI op against a plain PyTorch fp32 evaluation of the same op (tests/emu_ops.py), on
+fp16-rounded seeded inputs.  Tolerances: fp16-output ops 4e-3 of the output range (one fp16 rounding + fp32
+accumulation-order noise); fp32 ops 1e-4."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import emu_ops as E
+from common import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def ops():
+    from mgld_vsr_b200 import ops as O
+    return O
+
+
+def rnd(*s, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(s))
+    return (torch.randn(*s, generator=g) * scale).to(DEV)
+
+
+@pytest.mark.parametrize("M,K,N,kw", [
+    (256, 64, 128, {}), (1024, 320, 320, {}), (20480, 320, 960, {}), (77, 1024, 640, {}), (512, 128, 32, {}),
+    (1000, 1280, 1280, dict(res=True)), (640, 512, 256, dict(f32=True, act=2)), (2048, 640, 1280, dict(act=4, bn=128)),
+    (300, 200, 512, {}),      # K tail (200 = 3*64 + 8): TMA zero fill
+])
+def test_gemm(M, K, N, kw):
+    O = ops()
+    a, w = rnd(M, K).half(), rnd(N, K, scale=K ** -0.5).half()
+    b = rnd(N)
+    r = rnd(M, N).half() if kw.get("res") else None
+    args = dict(bias=b, act=kw.get("act", 0), res=r, alpha=0.5 if r is not None else 1.0, beta=2.0 if r is not None else 0.0,
+                out_f32=kw.get("f32", False))
+    got = O.conv_gemm(a, w, block_n=kw.get("bn", 0), **args)
+    ref = E.conv_gemm(a, w, **args)
+    assert rel_err(got, ref) < 4e-3
+
+
+@pytest.mark.parametrize("T,H,W,Ci,Co,two", [(2, 16, 16, 64, 64, False), (5, 64, 64, 320, 320, False),
+                                            (5, 8, 8, 1280, 1280, False), (5, 32, 32, 960, 640, True),
+                                            (3, 30, 46, 128, 256, False), (1, 120, 120, 128, 128, False)])
+def test_conv3x3(T, H, W, Ci, Co, two):
+    O = ops()
+    x = rnd(T, H, W, Ci).half()
+    w = O.pack_conv_weight(rnd(Co, Ci, 3, 3, scale=(9 * Ci) ** -0.5))
+    b = rnd(Co)
+    if two:
+        c1 = (Ci // 128) * 64
+        a, a2 = x[..., :c1].contiguous(), x[..., c1:].contiguous()
+    else:
+        a, a2 = x, None
+    got = O.conv_gemm(a, w, taps=9, a2=a2, bias=b)
+    ref = E.conv_gemm(a, w, taps=9, a2=a2, bias=b)
+    assert rel_err(got, ref) < 4e-3
+
+
+def test_conv_strided_views_and_column_offset():
+    """the RDB usage: A is a channel-prefix view of a wider buffer, the output lands in a column slot of it"""
+    O = ops()
+    T, H, W, C = 2, 16, 24, 128
+    buf = torch.zeros(T, H, W, C + 256, device=DEV, dtype=torch.float16)
+    buf[..., :C + 64] = rnd(T, H, W, C + 64).half()
+    w = O.pack_conv_weight(rnd(32, C + 64, 3, 3, scale=0.03))
+    b = rnd(32)
+    ref_buf = buf.clone()
+    O.conv_gemm(buf[..., :C + 64], w, taps=9, bias=b, act=O.ACT_LRELU02, out=buf, out_col0=C + 64, block_n=32)
+    E.conv_gemm(ref_buf[..., :C + 64], w, taps=9, bias=b, act=E.ACT_LRELU02, out=ref_buf, out_col0=C + 64)
+    assert rel_err(buf, ref_buf) < 4e-3
+    assert torch.equal(buf[..., C + 96:], ref_buf[..., C + 96:])     # untouched slots stay zero
+
+
+@pytest.mark.parametrize("T,H,W,C", [(5, 8, 8, 1280), (5, 32, 32, 256), (2, 12, 20, 128)])
+def test_temporal_conv(T, H, W, C):
+    O = ops()
+    x = rnd(T, H, W, C).half()
+    w = O.pack_temporal_weight(rnd(C, C, 3, 1, 1, scale=(3 * C) ** -0.5))
+    b = rnd(C)
+    kw = dict(taps=3, bias=b, alpha=0.3, beta=0.7, res=x)
+    assert rel_err(O.conv_gemm(x, w, **kw), E.conv_gemm(x, w, **kw)) < 4e-3
+
+
+def test_geglu_and_spade_epilogues():
+    O = ops()
+    a = rnd(4096, 320).half()
+    w, b = rnd(2560, 320, scale=320 ** -0.5).half(), rnd(2560)
+    wp, bp = O.interleave_pair(w[:1280], w[1280:]), O.interleave_pair(b[:1280], b[1280:])
+    got = O.conv_gemm(a, wp, bias=bp, epilogue=O.EPI_GEGLU)
+    y = a.float() @ w.float().t() + b
+    assert rel_err(got, y[:, :1280] * F.gelu(y[:, 1280:])) < 4e-3
+    T, H, W, Ch, C = 5, 16, 16, 128, 640
+    actv, h, res = rnd(T, H, W, Ch).half(), rnd(T, H, W, C).half(), rnd(T, H, W, C).half()
+    wg, wb = O.pack_conv_weight(rnd(C, Ch, 3, 3, scale=0.03)), O.pack_conv_weight(rnd(C, Ch, 3, 3, scale=0.03, seed=5))
+    bg, bb, gw, gb = rnd(C, scale=0.1), rnd(C, scale=0.1, seed=3), rnd(C, seed=7), rnd(C, seed=9)
+    st = O.gn_finalize(O.gn_stats(h), H * W, C, 1e-5)
+    kw = dict(taps=9, bias=O.interleave_pair(bg, bb), epilogue=O.EPI_SPADE, h=h, gn_stats=st, gn_weight=gw, gn_bias=gb,
+              groups=32, res=res, beta=1.0)
+    wp = O.interleave_pair(wg, wb)
+    assert rel_err(O.conv_gemm(actv, wp, **kw), E.conv_gemm(actv, wp, **kw)) < 4e-3
+
+
+@pytest.mark.parametrize("B,N,heads,dh,mode", [(1, 128, 1, 64, "self"), (5, 4096, 5, 64, "self"), (5, 1024, 10, 64, "self"),
+                                              (5, 64, 20, 64, "self"), (2, 200, 3, 64, "self"), (5, 4096, 5, 64, "cross"),
+                                              (5, 64, 20, 64, "cross"), (5, 4096, 4, 64, "legacy"), (5, 256, 4, 128, "legacy"),
+                                              (5, 64, 4, 128, "legacy")])
+def test_attention(B, N, heads, dh, mode):
+    O = ops()
+    C = heads * dh
+    if mode == "cross":
+        q, kv = rnd(B * N, C).half(), rnd(77, 2 * C).half()
+        kw = dict(batch=B, heads=heads, head_dim=dh, nq=N, nkv=77, scale=dh ** -0.5, k_col0=0, v_col0=C, kv_batched=False)
+        got, ref = O.attention(q, kv, kv, **kw), E.attention(q.cpu(), kv.cpu(), kv.cpu(), **kw)
+    else:
+        qkv = rnd(B * N, 3 * C).half()
+        if mode == "self":
+            kw = dict(q_col0=0, k_col0=C, v_col0=2 * C)
+        else:
+            kw = dict(q_col0=0, k_col0=dh, v_col0=2 * dh, q_head_stride=3 * dh, k_head_stride=3 * dh, v_head_stride=3 * dh)
+        kw.update(batch=B, heads=heads, head_dim=dh, nq=N, nkv=N, scale=dh ** -0.5)
+        got = O.attention(qkv, qkv, qkv, **kw)
+        x = qkv.float().reshape(B, N, 3, heads, dh) if mode == "self" else qkv.float().reshape(B, N, heads, 3, dh).transpose(2, 3)
+        q, k, v = [x[:, :, i].transpose(1, 2) for i in range(3)]
+        ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * N, C)
+    assert rel_err(got.cpu(), ref.cpu()) < 4e-3
+
+
+@pytest.mark.parametrize("T,HW,C1,C2", [(5, 4096, 320, 0), (5, 1024, 1280, 640), (2, 64, 64, 0), (3, 900, 128, 128),
+                                       (5, 256, 2560, 0)])
+def test_groupnorm(T, HW, C1, C2):
+    O = ops()
+    x1 = (rnd(T, HW, C1) * 2 + 0.5).half()
+    x2 = rnd(T, HW, C2).half() if C2 else None
+    g, b = rnd(C1 + C2), rnd(C1 + C2, seed=2)
+    sums = O.gn_stats(x1, x2)
+    assert rel_err(sums, E.gn_stats(x1, x2)) < 1e-5
+    assert rel_err(O.gn_apply(x1, sums, 1e-5, g, b, True, x2=x2), E.gn_apply(x1, sums, 1e-5, g, b, True, x2=x2)) < 3e-3
+    assert rel_err(O.gn_apply(x1, sums, 1e-6, None, None, False, x2=x2), E.gn_apply(x1, sums, 1e-6, None, None, False, x2=x2)) < 3e-3
+    assert rel_err(O.gn_finalize(sums, HW, C1 + C2, 1e-5), E.gn_finalize(sums, HW, C1 + C2, 1e-5)) < 1e-5
+
+
+@pytest.mark.parametrize("M,C", [(20480, 320), (5120, 640), (333, 1280), (7, 64)])
+def test_layernorm(M, C):
+    O = ops()
+    x, g, b = (rnd(M, C) * 3 + 1).half(), rnd(C), rnd(C, seed=4)
+    assert rel_err(O.layernorm(x, g, b), E.layernorm(x, g, b)) < 3e-3
+
+
+def test_softmax_rows_and_small_ops():
+    O = ops()
+    s = rnd(300, 1000) * 20
+    assert rel_err(O.softmax_rows(s, 0.044), E.softmax_rows(s, 0.044)) < 2e-3
+    x = rnd(3, 5, 17, 23)
+    assert torch.equal(O.nchw_to_nhwc(x), E.nchw_to_nhwc(x))
+    xh = rnd(2, 9, 13, 64).half()
+    assert torch.equal(O.nhwc_to_nchw(xh), E.nhwc_to_nchw(xh))
+    assert torch.equal(O.upsample2x(xh), E.upsample2x(xh))
+    for pad in (0, 1):
+        assert torch.equal(O.im2col_s2(xh, pad), E.im2col_s2(xh, pad))
+    xe = rnd(2, 10, 14, 64).half()
+    for pad in (0, 1):
+        assert torch.equal(O.im2col_s2(xe, pad), E.im2col_s2(xe, pad))
+    y = rnd(2, 9, 13, 64, seed=8).half()
+    assert rel_err(O.axpby(xh, y, 1.0, 0.7), E.axpby(xh, y, 1.0, 0.7)) < 2e-3
+
+
+def test_stem_and_head_convs():
+    O = ops()
+    x = rnd(2, 4, 20, 28)
+    w, b = rnd(64, 4, 3, 3, scale=0.2), rnd(64)
+    assert rel_err(O.conv_small_cin(x, w, b), E.conv_small_cin(x, w, b)) < 2e-3
+    w1, b1 = rnd(8, 8, 1, 1, scale=0.3), rnd(8)
+    x8 = rnd(2, 8, 9, 11)
+    assert rel_err(O.conv_small_f32(x8, w1, b1), E.conv_small_f32(x8, w1, b1)) < 1e-5
+    xh = rnd(2, 12, 10, 320).half()
+    for co in (3, 4, 8):
+        wp, bb = O.pack_conv_weight(rnd(co, 320, 3, 3, scale=0.02)), rnd(co)
+        assert rel_err(O.conv3x3_small_cout(xh, wp, bb), E.conv3x3_small_cout(xh, wp, bb)) < 1e-4
+
+
+def test_time_embedding_gemv_temporal_attention_gaussian():
+    O = ops()
+    t = torch.tensor([937.0], device=DEV)
+    assert rel_err(O.timestep_embedding(t, 320), E.timestep_embedding(t.cpu(), 320).to(DEV)) < 1e-5
+    x, w, b, a = rnd(1280), rnd(640, 1280, scale=0.03).half(), rnd(640), rnd(640, seed=3)
+    assert rel_err(O.gemv(x, w, b, a, True, False), E.gemv(x, w, b, a, True, False)) < 1e-4
+    assert rel_err(O.gemv(x, w, b, None, False, True), E.gemv(x, w, b, None, False, True)) < 1e-4
+    qkv = rnd(5, 64, 3 * 1280).half()
+    assert rel_err(O.temporal_attention(qkv, 20, 0.125), E.temporal_attention(qkv, 20, 0.125)) < 3e-3
+    m, n = rnd(2, 8, 6, 7), rnd(2, 4, 6, 7, seed=1)
+    assert rel_err(O.gaussian_sample(m, n, 0.18215), E.gaussian_sample(m, n, 0.18215)) < 1e-6
+
+
+def test_flow_ops():
+    O = ops()
+    for (n, c, h, w) in [(4, 4, 64, 64), (2, 3, 37, 53), (1, 2, 136, 240)]:
+        x = rnd(n, c, h, w)
+        fl = F.interpolate(rnd(n, 2, 8, 8) * 3, size=(h, w), mode="bicubic")
+        flp = fl.permute(0, 2, 3, 1).contiguous()
+        for border in (False, True):
+            assert rel_err(O.flow_warp_f32(x, flp, 0, border=border), E.flow_warp_f32(x.cpu(), flp.cpu(), 0, border=border).to(DEV)) < 1e-4
+        assert rel_err(O.flow_warp_f32(x, fl, 1), E.flow_warp_f32(x.cpu(), fl.cpu(), 1).to(DEV)) < 1e-4
+        oh, ow = h // 2 + 3, w // 2 + 1
+        assert rel_err(O.resize_flow_f32(fl, oh, ow), E.resize_flow_f32(fl, oh, ow)) < 1e-5
+
+
+@pytest.mark.parametrize("t,c,h,w", [(5, 4, 64, 64), (5, 4, 136, 240), (2, 4, 32, 48), (3, 4, 20, 28), (1, 4, 16, 16)])
+def test_guidance(t, c, h, w):
+    O = ops()
+    z = rnd(t, c, h, w)
+    if t == 1:
+        out = O.motion_guidance_f32(z, None, None, None, None, 3.0)
+        assert torch.equal(out, z)
+        return
+    ff = F.interpolate(rnd(t - 1, 2, 8, 8) * 1.5, size=(h, w), mode="bicubic")
+    fb = -ff + 0.3 * F.interpolate(rnd(t - 1, 2, 8, 8, seed=3), size=(h, w), mode="bicubic")
+    fo, bo = O.fb_consistency_f32(fb, ff)
+    rfo, rbo = E.fb_consistency_f32(fb.cpu(), ff.cpu())
+    assert ((fo.cpu() != rfo).float().mean() + (bo.cpu() != rbo).float().mean()).item() < 1e-4
+    assert 0.02 < fo.mean().item() < 0.98                      # masks are genuinely mixed
+    out, loss, g = O.motion_guidance_f32(z, ff, fb, fo, bo, 32.0, want_loss=True)
+    rout, rloss, rg = E.motion_guidance_f32(z.cpu(), ff.cpu(), fb.cpu(), fo.cpu(), bo.cpu(), 32.0, want_loss=True)
+    assert rel_err(loss.cpu(), rloss) < 1e-5 and rel_err(g.cpu(), rg) < 1e-4 and rel_err(out.cpu(), rout) < 1e-5
+
+
+def test_canvas_posterior():
+    O = ops()
+    from oracle.torch_ref import canvas_tiles, gaussian_weights
+    T, C, h, w, ts = 2, 4, 92, 120, 64
+    x, noise = rnd(T, C, h, w), rnd(T, C, h, w, seed=5)
+    offs = canvas_tiles(h, w, ts, 32)
+    tiles = [rnd(T, C, ts, ts, seed=10 + i) for i in range(len(offs))]
+    tw = gaussian_weights(ts, ts, 1)[0, 0].to(DEV)
+    args = (offs, ts, 1.7, 1.3, 0.4, 0.6, 0.25)
+    got, ge = O.canvas_posterior_f32(x, tiles, tw, noise, *args, want_eps=True)
+    ref, re_ = E.canvas_posterior_f32(x, tiles, tw, noise, *args, want_eps=True)
+    assert rel_err(ge, re_) < 1e-6 and rel_err(got, ref) < 1e-6
