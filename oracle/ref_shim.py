@@ -97,6 +97,8 @@ def install():
 
     _mod("omegaconf", ListConfig=ListConfig, DictConfig=DictConfig, OmegaConf=None)
     _mod("omegaconf.listconfig", ListConfig=ListConfig)
+    # (3b) skimage (imported by scripts/util_image.py:14 for I/O helpers the hot path never calls)
+    _mod("skimage", img_as_ubyte=lambda a: a, img_as_float32=lambda a: a)
     # (4) matplotlib
     _mod("matplotlib")
     _mod("matplotlib.pyplot")

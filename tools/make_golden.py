@@ -1,0 +1,89 @@
+"""Generate tests/golden/*.pt from the UNMODIFIED reference modules (imported from /root/reference through
+oracle/ref_shim.py).  Run in the build container only; the fixtures are small output tensors — weights and inputs are
+re-derived on the fly from parameter names (tests/common.py:det_state_dict / det_tensor), so nothing large is stored.
+
+    python tools/make_golden.py
+"""
+import contextlib
+import io
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+import torch.nn.functional as F
+
+from common import GOLDEN, TINY_DD, TINY_STRUCT, TINY_UNET, det_state_dict, det_tensor
+from oracle import ref_shim
+
+T = 2
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    ref_shim.install()
+    om = ref_shim.ref("ldm.modules.diffusionmodules.openaimodel")
+    ae = ref_shim.ref("ldm.models.autoencoder")
+    au = ref_shim.ref("basicsr.archs.arch_util")
+    uf = ref_shim.ref("scripts.util_flow")
+    with torch.no_grad():
+        # --- UNet + struct encoder ---------------------------------------------------------------------------------
+        unet = quiet(om.InflatedUNetModelDualcondV2, **TINY_UNET).eval()
+        unet.load_state_dict(det_state_dict({k: v.shape for k, v in unet.state_dict().items()}))
+        se = quiet(om.InflatedEncoderUNetModelWT, **TINY_STRUCT).eval()
+        se.load_state_dict(det_state_dict({k: v.shape for k, v in se.state_dict().items()}))
+        x, lat = det_tensor("x", (T, 4, 32, 32)), det_tensor("lat", (T, 4, 32, 32))
+        ctx, t = det_tensor("ctx", (1, 77, 128)), torch.tensor([500])
+        sc = {"32": det_tensor("s32", (T, 64, 32, 32)), "16": det_tensor("s16", (T, 64, 16, 16))}
+        torch.save({"eps": unet(x, t, ctx, sc), "struct": {k: v.half() for k, v in se(lat, t).items()},
+                    "eps_chained": unet(x, t, ctx, se(lat, t))},
+                   os.path.join(GOLDEN, "tiny_unet.pt"))
+        # --- VAEs ----------------------------------------------------------------------------------------------------
+        vq = quiet(ae.VideoAutoencoderKLResi, ddconfig=TINY_DD, lossconfig={"target": "torch.nn.Identity"}, embed_dim=4).eval()
+        vq.load_state_dict(det_state_dict({k: v.shape for k, v in vq.state_dict().items()}))
+        img, z = det_tensor("img", (T, 3, 64, 64)).clamp(-1, 1), det_tensor("z", (T, 4, 8, 8))
+        post, fea = vq.encode(img)
+        kl = quiet(ae.AutoencoderKL, ddconfig=TINY_DD, lossconfig={"target": "torch.nn.Identity"}, embed_dim=4).eval()
+        kl.load_state_dict(det_state_dict({k: v.shape for k, v in kl.state_dict().items()}))
+        torch.save({"moments": post.parameters, "fea_mean": [f.mean(dim=(2, 3)) for f in fea], "dec": vq.decode(z, fea),
+                    "kl_moments": kl.encode(img).parameters}, os.path.join(GOLDEN, "tiny_vae.pt"))
+        # --- flow ops -------------------------------------------------------------------------------------------------
+        h, w = 40, 56
+        xf = det_tensor("fx", (3, 4, h, w))
+        fl = F.interpolate(det_tensor("flow", (3, 2, 6, 7)) * 3.0, size=(h, w), mode="bicubic")
+        fl2 = -fl + 0.4 * F.interpolate(det_tensor("flow2", (3, 2, 6, 7)), size=(h, w), mode="bicubic")
+        fo, bo = uf.forward_backward_consistency_check(fl, fl2, alpha=0.01, beta=0.5)
+        torch.save({"warp": au.flow_warp(xf, fl.permute(0, 2, 3, 1)),
+                    "warp_border": au.flow_warp(xf, fl.permute(0, 2, 3, 1), padding_mode="border"),
+                    "warp_nearest": au.flow_warp(xf, fl.permute(0, 2, 3, 1), interp_mode="nearest"),
+                    "resize": au.resize_flow(fl, "shape", (23, 31)), "fwd_occ": fo, "bwd_occ": bo},
+                   os.path.join(GOLDEN, "flow_ops.pt"))
+    # --- guidance (reference's own compute_temporal_condition_v4 + autograd) ----------------------------------------
+    dd = ref_shim.ref("ldm.models.diffusion.ddpm")
+    Tn = 4
+    stub = type("S", (), {"num_frames": Tn})()
+    z = det_tensor("gz", (Tn, 4, h, w))
+    ff = F.interpolate(det_tensor("gff", (Tn - 1, 2, 6, 7)) * 1.5, size=(h, w), mode="bicubic")[None]
+    fb = (-ff + 0.3 * F.interpolate(det_tensor("gfb", (Tn - 1, 2, 6, 7)), size=(h, w), mode="bicubic")[None])
+    occs = [uf.forward_backward_consistency_check(fb[:, i], ff[:, i]) for i in range(Tn - 1)]
+    fo = torch.stack([o[0][:, None] for o in occs], 1)
+    bo = torch.stack([o[1][:, None] for o in occs], 1)
+    zr = z.clone().requires_grad_(True)
+    loss = dd.LatentDiffusionVSRTextWT.compute_temporal_condition_v4(stub, (ff, fb), zr, (fo, bo))
+    g = torch.autograd.grad(loss, zr)[0]
+    step = -10.0 * -2.3
+    torch.save({"loss": loss.detach(), "grad": g, "out": (z - step * g).detach(), "step": step, "fwd_occ": fo, "bwd_occ": bo},
+               os.path.join(GOLDEN, "guidance.pt"))
+    for f in sorted(os.listdir(GOLDEN)):
+        print(f, os.path.getsize(os.path.join(GOLDEN, f)))
+
+
+if __name__ == "__main__":
+    main()
