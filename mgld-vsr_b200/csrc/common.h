@@ -51,6 +51,9 @@ bool initialised();
 // the inner box is narrower (64B -> SWIZZLE_64B, 32B -> SWIZZLE_32B).
 int make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box, const uint32_t* elem_strides = nullptr);
+// same for fp32 tensors (inner box must be 32 elements = 128 bytes)
+int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -1,13 +1,18 @@
-// Implicit-GEMM convolution / linear layer for sm_100a.
+// Implicit-GEMM convolution / linear layer for sm_100a — persistent, warp-specialised, TMA in / TMA out.
 //
 //   out[m, n] = epilogue( sum_{tap, c} A[pixel(m) + off(tap), c] * W[n, tap*C + c] )
 //
-// One CTA computes a 128 x BLOCK_N output tile.  The 128 rows of a tile are a (BW x BH x BT) box of pixels of the
-// NHWC activation, so for every filter tap the A operand is ONE TMA box load at shifted coordinates — the TMA unit
-// does the im2col, and its out-of-bounds zero fill is the convolution's zero padding (spatial and temporal).
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + tcgen05.mma issuer, warps 2-5 = epilogue
-// (TMEM -> registers -> fp32 staging in the drained pipeline smem -> coalesced 16-byte global stores with the fused
-// bias / activation / residual / GEGLU / SPADE math).
+// A tile is 128 output pixels x BLOCK_N channels.  The 128 rows are a (BW x BH x BT) box of pixels of the NHWC
+// activation, so for every filter tap the A operand is ONE TMA box load at shifted coordinates: the TMA unit does the
+// im2col and its out-of-bounds zero fill is the convolution's zero padding (spatial and temporal).  The same box
+// geometry is used by the epilogue's TMA loads (residual / SPADE input) and TMA stores, which also clip partial tiles.
+//
+// Each CTA (one per SM) loops over tiles.  Warp roles:
+//   warp 0     TMA producer: A/B ring (3-6 stages) + the residual tile of the current output tile
+//   warp 1     tcgen05.mma issuer; the fp32 accumulator is double-buffered in TMEM (2 x BLOCK_N columns), so the
+//              mainloop of tile i+1 overlaps the epilogue of tile i
+//   warps 2-5  epilogue: thread == accumulator row.  tcgen05.ld 32 columns at a time -> (+bias, activation, residual /
+//              GEGLU / SPADE math in fp32) -> fp16 -> 128B-swizzled staging tile in smem -> one TMA store per 64 columns
 //
 // Replaces (reference file:line): F.conv2d in ResBlockDual openaimodel.py:401-445, SPADE spade.py:83-88,
 // VAE ResnetBlock model.py:134-161; nn.Linear in attention.py:48-75,510-524; Conv3d(3,1,1) util.py:291-310.
@@ -22,76 +27,126 @@ namespace mgld {
 constexpr int kBlockM = 128;
 constexpr int kKChunk = 64;  // fp16 elements per K step = one 128-byte swizzle row
 constexpr int kABytes = kBlockM * kKChunk * 2;
+constexpr int kPanelBytes = kBlockM * 128;  // one staging panel: 128 rows x 128 bytes (64 fp16 or 32 fp32 columns)
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;
 
 struct ConvGemmParams {
   int T, H, W;
   int BW, BH, BT;
-  int tiles_w, tiles_h, tiles_t;
+  int tiles_w, tiles_h, tiles_t, tiles_m, tiles_n;
   int kchunks1, kchunks;  // 64-wide chunks in source 1 / in both sources (per tap)
   int taps;
-  int N, block_n, n_stage_cols, n_out_tile, n_out_total;
-  int stages, tmem_cols;
-  int epilogue, act;
+  int N, block_n, n_out_tile, n_out_total, n_panels;
+  int stages, tmem_cols, acc_stride;
+  int panel_cols;  // fp16 output columns per staging panel: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B)
+  int epilogue, act, has_res, out_f32;
   const float* bias;
   float alpha, beta;
-  const __half* res;
-  int ldres;
-  const __half* h;
-  int ldh;
   const float* gn_stats;
   const float* gn_weight;
   const float* gn_bias;
   int groups, ch_per_group;
-  void* out;
-  int ldout, out_col0, out_f32;
+  uint32_t off_staging, off_hstage, off_bias;  // byte offsets from the 1024-aligned smem base
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
+__device__ __forceinline__ void act_inplace32(float* v, int act) {
   switch (act) {
-    case MGLD_ACT_RELU: return fmaxf(v, 0.f);
-    case MGLD_ACT_SILU: return v / (1.f + __expf(-v));
-    case MGLD_ACT_LRELU02: return v > 0.f ? v : 0.2f * v;
-    case MGLD_ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
-    default: return v;
+    case MGLD_ACT_RELU:
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+      break;
+    case MGLD_ACT_SILU:
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = v[i] / (1.f + __expf(-v[i]));
+      break;
+    case MGLD_ACT_LRELU02:
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : 0.2f * v[i];
+      break;
+    case MGLD_ACT_GELU:
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
+      break;
+    default: break;
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+// 16-byte chunk `chunk` (0..3) of the 32 consecutive fp16 columns [c0, c0+32) of row `row` in the swizzled staging
+// tile.  PANEL = 64: 128-byte rows, chunk ^= row & 7 (TMA SWIZZLE_128B); PANEL = 32: 64-byte rows, chunk ^= (row >> 1) & 3
+// (TMA SWIZZLE_64B) — used when BLOCK_N is an odd multiple of 32 (e.g. 160 for the 320-channel layers).
+__device__ __forceinline__ uint8_t* stage_ptr16(uint8_t* staging, int row, int c0, int chunk, int panel_cols) {
+  if (panel_cols == 64)
+    return staging + (c0 >> 6) * kPanelBytes + row * 128 + (((((c0 & 63) >> 3) + chunk) ^ (row & 7)) << 4);
+  return staging + (c0 >> 5) * (kPanelBytes / 2) + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
+}
+__device__ __forceinline__ void load_stage32(uint8_t* staging, int row, int c0, float* r, int panel_cols) {
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    const uint4 v = *reinterpret_cast<const uint4*>(stage_ptr16(staging, row, c0, ch, panel_cols));
+    const __half2* hh = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 f = __half22float2(hh[u]);
+      r[ch * 8 + 2 * u] = f.x;
+      r[ch * 8 + 2 * u + 1] = f.y;
+    }
+  }
+}
+__device__ __forceinline__ void store_stage32(uint8_t* staging, int row, int c0, const float* o, int panel_cols) {
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    uint4 pk;
+    pk.x = pack_h2(o[ch * 8 + 0], o[ch * 8 + 1]);
+    pk.y = pack_h2(o[ch * 8 + 2], o[ch * 8 + 3]);
+    pk.z = pack_h2(o[ch * 8 + 4], o[ch * 8 + 5]);
+    pk.w = pack_h2(o[ch * 8 + 6], o[ch * 8 + 7]);
+    *reinterpret_cast<uint4*>(stage_ptr16(staging, row, c0, ch, panel_cols)) = pk;
+  }
+}
+// fp32 output: panel = 32 columns (128 bytes) -> 8 chunks of 16 bytes
+__device__ __forceinline__ void store_stage32_f32(uint8_t* staging, int row, int c0, const float* o) {
+  uint8_t* base = staging + (c0 >> 5) * kPanelBytes + row * 128;
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch)
+    *reinterpret_cast<float4*>(base + ((ch ^ (row & 7)) << 4)) =
+        make_float4(o[ch * 4], o[ch * 4 + 1], o[ch * 4 + 2], o[ch * 4 + 3]);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                 const __grid_constant__ CUtensorMap tmB, const ConvGemmParams p) {
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                 const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmH,
+                 const ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], res_full, staging_free;
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const int b_bytes = p.block_n * kKChunk * 2;
-  const int stage_bytes = kABytes + b_bytes;
-
-  // tile coordinates: blockIdx.x enumerates pixel boxes (w fastest), blockIdx.y the N tiles
-  const int tile_m = blockIdx.x;
-  const int tw = tile_m % p.tiles_w;
-  const int th = (tile_m / p.tiles_w) % p.tiles_h;
-  const int tt = tile_m / (p.tiles_w * p.tiles_h);
-  const int x0 = tw * p.BW, y0 = th * p.BH, t0 = tt * p.BT;
-  const int n0 = blockIdx.y * p.block_n;
-  const int num_iters = p.taps * p.kchunks;
+  const int stage_bytes = kABytes + p.block_n * kKChunk * 2;
+  const int num_k = p.taps * p.kchunks;
+  const int total_tiles = p.tiles_m * p.tiles_n;
+  const bool pair_spade = p.epilogue == MGLD_EPI_SPADE;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (p.kchunks1 < p.kchunks) tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmOut);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    mbar_init(smem_u32(&tmem_full_bar), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&acc_full[b]), 1);
+      mbar_init(smem_u32(&acc_empty[b]), 128);
+    }
+    mbar_init(smem_u32(&res_full), 1);
+    mbar_init(smem_u32(&staging_free), 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), p.tmem_cols);
@@ -100,24 +155,50 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
+  // tile -> coordinates; consecutive tiles share the weight tile (n) and walk the pixel boxes (L2-friendly)
+  auto tile_coords = [&](int tile, int& x0, int& y0, int& t0, int& nt) {
+    const int tm = tile % p.tiles_m;
+    nt = tile / p.tiles_m;
+    x0 = (tm % p.tiles_w) * p.BW;
+    y0 = ((tm / p.tiles_w) % p.tiles_h) * p.BH;
+    t0 = (tm / (p.tiles_w * p.tiles_h)) * p.BT;
+  };
+
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
-      int it = 0;
-      for (int tap = 0; tap < p.taps; ++tap) {
-        int dx = 0, dy = 0, dt = 0;
-        if (p.taps == 9) { dx = tap % 3 - 1; dy = tap / 3 - 1; }
-        else if (p.taps == 3) { dt = tap - 1; }
-        for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
-          const uint32_t fb = smem_u32(&full_bar[s]);
-          const uint32_t sa = smem_base + s * stage_bytes;
-          mbar_expect_tx(fb, stage_bytes);
-          if (kc < p.kchunks1) tma_load_4d(sa, &tmA, fb, kc * kKChunk, x0 + dx, y0 + dy, t0 + dt);
-          else tma_load_4d(sa, &tmA2, fb, (kc - p.kchunks1) * kKChunk, x0 + dx, y0 + dy, t0 + dt);
-          tma_load_2d(sa + kABytes, &tmB, fb, it * kKChunk, n0);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        int x0, y0, t0, nt;
+        tile_coords(tile, x0, y0, t0, nt);
+        const int n0 = nt * p.block_n;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          int dx = 0, dy = 0, dt = 0;
+          if (p.taps == 9) { dx = tap % 3 - 1; dy = tap / 3 - 1; }
+          else if (p.taps == 3) { dt = tap - 1; }
+          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (it / p.stages) & 1;
+            mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+            const uint32_t fb = smem_u32(&full_bar[s]);
+            const uint32_t sa = smem_base + s * stage_bytes;
+            mbar_expect_tx(fb, stage_bytes);
+            if (kc < p.kchunks1) tma_load_4d(sa, &tmA, fb, kc * kKChunk, x0 + dx, y0 + dy, t0 + dt);
+            else tma_load_4d(sa, &tmA2, fb, (kc - p.kchunks1) * kKChunk, x0 + dx, y0 + dy, t0 + dt);
+            tma_load_2d(sa + kABytes, &tmB, fb, (tap * p.kchunks + kc) * kKChunk, n0);
+          }
+        }
+        if (p.has_res || pair_spade) {
+          // residual (and SPADE's h) tile of THIS output tile, into the staging buffers the epilogue will overwrite
+          mbar_wait(smem_u32(&staging_free), (lt & 1) ^ 1);
+          const uint32_t rb = smem_u32(&res_full);
+          const int c0 = nt * p.n_out_tile;
+          const int np = p.has_res ? p.n_panels : 0;
+          mbar_expect_tx(rb, np * (p.panel_cols == 32 ? kPanelBytes / 2 : kPanelBytes) + (pair_spade ? kPanelBytes : 0));
+          const int pbytes = p.panel_cols == 32 ? kPanelBytes / 2 : kPanelBytes;
+          for (int q = 0; q < np; ++q)
+            tma_load_4d(smem_base + p.off_staging + q * pbytes, &tmRes, rb, c0 + q * p.panel_cols, x0, y0, t0);
+          if (pair_spade) tma_load_4d(smem_base + p.off_hstage, &tmH, rb, c0, x0, y0, t0);
         }
       }
     }
@@ -125,150 +206,139 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ============================ MMA issuer ============================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16(kBlockM, p.block_n, 0, 0);
-      for (int it = 0; it < num_iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(smem_u32(&full_bar[s]), ph);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(smem_u32(&acc_empty[buf]), ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t sa = smem_base + s * stage_bytes;
-        const uint64_t adesc = umma_smem_desc(sa, 0, 1024, kSwz128);
-        const uint64_t bdesc = umma_smem_desc(sa + kABytes, 0, 1024, kSwz128);
+        const uint32_t dcol = tmem_base + buf * p.acc_stride;
+        for (int k = 0; k < num_k; ++k, ++it) {
+          const int s = it % p.stages;
+          mbar_wait(smem_u32(&full_bar[s]), (it / p.stages) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * stage_bytes;
+          const uint64_t adesc = umma_smem_desc(sa, 0, 1024, kSwz128);
+          const uint64_t bdesc = umma_smem_desc(sa + kABytes, 0, 1024, kSwz128);
 #pragma unroll
-        for (int k = 0; k < kKChunk / 16; ++k) {
-          // advance 32 bytes (16 fp16) along K inside the 128-byte swizzle row: +2 in the (addr>>4) field
-          umma_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+          for (int kk = 0; kk < kKChunk / 16; ++kk)
+            umma_ss(dcol, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0);  // +32 B along K per step
+          umma_commit(smem_u32(&empty_bar[s]));
         }
-        umma_commit(smem_u32(&empty_bar[s]));
+        umma_commit(smem_u32(&acc_full[buf]));
       }
-      umma_commit(smem_u32(&tmem_full_bar));
     }
   } else {
     // ============================ epilogue (warps 2..5) ============================
-    const int q = warp & 3;           // TMEM lane quadrant this warp may access
-    const int row = q * 32 + lane;    // tile row owned in phase 1
-    const int P = p.n_stage_cols + 4; // fp32 staging pitch
-    float* stage = reinterpret_cast<float*>(smem_gen);
-    mbar_wait(smem_u32(&tmem_full_bar), 0);
-    tc_fence_after();
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-
-    // ---- phase 1: TMEM -> registers -> (+bias, act / pair op) -> fp32 staging ----
-    if (p.epilogue == MGLD_EPI_GEGLU) {
-      for (int c0 = 0; c0 < 64; c0 += 16) {
-        uint32_t rv[16], rg[16];
-        tmem_ld_x16(trow + c0, rv);
-        tmem_ld_x16(trow + 64 + c0, rg);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float o[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int c = c0 + j + u;
-            float v = __uint_as_float(rv[j + u]);
-            float g = __uint_as_float(rg[j + u]);
-            if (p.bias) { v += __ldg(p.bias + n0 + c); g += __ldg(p.bias + n0 + 64 + c); }
-            o[u] = v * apply_act(g, MGLD_ACT_GELU);
-          }
-          *reinterpret_cast<float4*>(stage + row * P + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
-        }
-      }
-    } else {
-      const bool lin = (p.epilogue == MGLD_EPI_LINEAR);
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld_x16(trow + c0, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float o[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int n = n0 + c0 + j + u;
-            float v = __uint_as_float(r[j + u]);
-            if (p.bias && n < p.N) v += __ldg(p.bias + n);
-            if (lin) v = apply_act(v, p.act);
-            o[u] = v;
-          }
-          *reinterpret_cast<float4*>(stage + row * P + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
-        }
-      }
-    }
-    tc_fence_before();
-    named_bar_sync(1, 128);
-
-    // ---- phase 2: coalesced write-out with the tensor-valued epilogue terms ----
+    const int q = warp & 3;         // TMEM lane quadrant of this warp
+    const int row = q * 32 + lane;  // accumulator row == tile row
     const int e = threadIdx.x - 64;
-    const int vpr = p.n_out_tile >> 3;  // 8-column vectors per row
-    const int nout0 = blockIdx.y * p.n_out_tile;
-    const int total = kBlockM * vpr;
-    for (int idx = e; idx < total; idx += 128) {
-      const int r = idx / vpr;
-      const int v8 = idx - r * vpr;
-      const int col = nout0 + v8 * 8;
-      if (col >= p.n_out_total) continue;
-      const int x = x0 + r % p.BW;
-      const int y = y0 + (r / p.BW) % p.BH;
-      const int t = t0 + r / (p.BW * p.BH);
-      if (x >= p.W || y >= p.H || t >= p.T) continue;
-      const long long m = (static_cast<long long>(t) * p.H + y) * p.W + x;
-      float o[8];
-      const float* sp = stage + r * P + v8 * 8;
-      const float4 s0 = *reinterpret_cast<const float4*>(sp);
-      const float4 s1 = *reinterpret_cast<const float4*>(sp + 4);
-      o[0] = s0.x; o[1] = s0.y; o[2] = s0.z; o[3] = s0.w;
-      o[4] = s1.x; o[5] = s1.y; o[6] = s1.z; o[7] = s1.w;
-      float rs[8];
-      const bool has_res = (p.res != nullptr);
-      if (has_res) {
-        const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + m * p.ldres + col));
-        const __half2* hh = reinterpret_cast<const __half2*>(&rr);
+    uint8_t* staging = smem_gen + p.off_staging;
+    uint8_t* hstage = smem_gen + p.off_hstage;
+    float* bias_s = reinterpret_cast<float*>(smem_gen + p.off_bias);
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      int x0, y0, t0, nt;
+      tile_coords(tile, x0, y0, t0, nt);
+      const int buf = lt & 1;
+      const int n0 = nt * p.block_n;
+      // bias tile -> smem (all threads passed the previous tile's closing barrier, so bias_s is free)
+      for (int i = e; i < p.block_n; i += 128)
+        bias_s[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+      mbar_wait(smem_u32(&acc_full[buf]), (lt >> 1) & 1);
+      tc_fence_after();
+      if (p.has_res || pair_spade) mbar_wait(smem_u32(&res_full), lt & 1);
+      named_bar_sync(1, 128);
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * p.acc_stride;
+
+      if (p.epilogue == MGLD_EPI_LINEAR) {
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+          float v[32];
+          tmem_ld_x32(trow + c0, reinterpret_cast<uint32_t*>(v));
+          tmem_ld_wait();
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float2 f = __half22float2(hh[u]);
-          rs[2 * u] = f.x; rs[2 * u + 1] = f.y;
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(bias_s + c0 + i);
+            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+          }
+          act_inplace32(v, p.act);
+          if (p.has_res) {
+            float r[32];
+            load_stage32(staging, row, c0, r, p.panel_cols);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaf(p.alpha, v[i], p.beta * r[i]);
+          } else if (p.alpha != 1.f) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+          }
+          if (p.out_f32) store_stage32_f32(staging, row, c0, v);
+          else store_stage32(staging, row, c0, v, p.panel_cols);
+        }
+      } else if (p.epilogue == MGLD_EPI_GEGLU) {
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          float v[32], g[32];
+          tmem_ld_x32(trow + c0, reinterpret_cast<uint32_t*>(v));
+          tmem_ld_x32(trow + 64 + c0, reinterpret_cast<uint32_t*>(g));
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { v[i] += bias_s[c0 + i]; g[i] += bias_s[64 + c0 + i]; }
+          act_inplace32(g, MGLD_ACT_GELU);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= g[i];
+          if (p.has_res) {
+            float r[32];
+            load_stage32(staging, row, c0, r, p.panel_cols);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaf(p.alpha, v[i], p.beta * r[i]);
+          }
+          store_stage32(staging, row, c0, v, 64);
+        }
+      } else {  // SPADE: out = beta*res + GNaffine(h) * (1 + gamma) + beta_s
+        const int tt = min(t0 + row / (p.BW * p.BH), p.T - 1);
+        const int cbase = nt * 64;
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          float gm[32], bt[32], hv[32];
+          tmem_ld_x32(trow + c0, reinterpret_cast<uint32_t*>(gm));
+          tmem_ld_x32(trow + 64 + c0, reinterpret_cast<uint32_t*>(bt));
+          tmem_ld_wait();
+          load_stage32(hstage, row, c0, hv, 64);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = cbase + c0 + i;
+            const int g = c / p.ch_per_group;
+            const float2 st = __ldg(reinterpret_cast<const float2*>(p.gn_stats) + tt * p.groups + g);
+            const float xn = fmaf((hv[i] - st.x) * st.y, __ldg(p.gn_weight + c), __ldg(p.gn_bias + c));
+            gm[i] = fmaf(xn, 1.f + gm[i] + bias_s[c0 + i], bt[i] + bias_s[64 + c0 + i]);
+          }
+          if (p.has_res) {
+            float r[32];
+            load_stage32(staging, row, c0, r, p.panel_cols);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) gm[i] = fmaf(p.beta, r[i], gm[i]);
+          }
+          store_stage32(staging, row, c0, gm, 64);
         }
       }
-      if (p.epilogue == MGLD_EPI_SPADE) {
-        // staged: gamma at [0,64), beta at [64,128) of this tile; o[] currently holds gamma
-        const float4 b0 = *reinterpret_cast<const float4*>(sp + 64);
-        const float4 b1 = *reinterpret_cast<const float4*>(sp + 68);
-        const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        const uint4 hr = __ldg(reinterpret_cast<const uint4*>(p.h + m * p.ldh + col));
-        const __half2* hh = reinterpret_cast<const __half2*>(&hr);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int c = col + u;
-          const int g = c / p.ch_per_group;
-          const float mean = __ldg(p.gn_stats + (t * p.groups + g) * 2);
-          const float rstd = __ldg(p.gn_stats + (t * p.groups + g) * 2 + 1);
-          const float2 f = __half22float2(hh[u >> 1]);
-          const float hv = (u & 1) ? f.y : f.x;
-          const float xn = (hv - mean) * rstd * __ldg(p.gn_weight + c) + __ldg(p.gn_bias + c);
-          float val = xn * (1.f + o[u]) + bt[u];
-          if (has_res) val += p.beta * rs[u];
-          o[u] = val;
+      // accumulator buffer drained -> the MMA warp may start tile lt+2 in it
+      tc_fence_before();
+      mbar_arrive(smem_u32(&acc_empty[buf]));
+      // staging tile complete -> one thread issues the TMA stores
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (e == 0) {
+        const int c0 = nt * p.n_out_tile;
+        const int cols_per_panel = p.out_f32 ? 32 : p.panel_cols;
+        const int pbytes = (!p.out_f32 && p.panel_cols == 32) ? kPanelBytes / 2 : kPanelBytes;
+        for (int pn = 0; pn < p.n_panels; ++pn) {
+          if (c0 + pn * cols_per_panel < p.n_out_total)
+            tma_store_4d(&tmOut, smem_base + p.off_staging + pn * pbytes, c0 + pn * cols_per_panel, x0, y0, t0);
         }
-      } else {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          float val = p.alpha * o[u];
-          if (has_res) val += p.beta * rs[u];
-          o[u] = val;
-        }
+        tma_store_commit();
+        tma_store_wait_read();  // staging may be overwritten (by the next residual load / next tile's epilogue)
+        if (p.has_res || pair_spade) mbar_arrive(smem_u32(&staging_free));
       }
-      if (p.out_f32) {
-        float* op = reinterpret_cast<float*>(p.out) + m * p.ldout + p.out_col0 + col;
-        *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<float4*>(op + 4) = make_float4(o[4], o[5], o[6], o[7]);
-      } else {
-        uint4 pk;
-        pk.x = pack_h2(o[0], o[1]); pk.y = pack_h2(o[2], o[3]);
-        pk.z = pack_h2(o[4], o[5]); pk.w = pack_h2(o[6], o[7]);
-        __half* op = reinterpret_cast<__half*>(p.out) + m * p.ldout + p.out_col0 + col;
-        *reinterpret_cast<uint4*>(op) = pk;
-      }
+      named_bar_sync(1, 128);
     }
+    if (e == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -279,16 +349,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-static int pick_block_n(int N) {
-  if (N % 256 == 0) return 256;
-  if (N % 160 == 0) return 160;
-  if (N % 128 == 0) return 128;
-  if (N % 192 == 0) return 192;
-  if (N % 96 == 0) return 96;
-  if (N % 64 == 0) return 64;
-  if (N % 32 == 0) return 32;
-  if (N % 16 == 0) return 16;
-  return N <= 128 ? ((N + 15) / 16) * 16 : 128;
+static int pick_block_n(int N, int tiles_m, int sms) {
+  // widest tile that keeps the machine busy: cost ~ waves * (mainloop ~ bn + per-tile overhead)
+  const int cands[] = {256, 192, 160, 128, 96, 64, 32};
+  int best = 32;
+  double best_cost = 1e30;
+  for (int bn : cands) {
+    const int tn = ceil_div(N, bn);
+    const long long tiles = 1LL * tiles_m * tn;
+    const long long waves = (tiles + sms - 1) / sms;
+    const double cost = (double)waves * (bn + 32.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
 }
 
 // choose the pixel box (BW,BH,BT), BW*BH*BT = 128, minimising padded work
@@ -298,8 +371,7 @@ static void pick_box(int T, int H, int W, int* BW, int* BH, int* BT) {
     for (int bh = 128 / bw; bh >= 1; bh >>= 1) {
       const int bt = 128 / (bw * bh);
       const long long cost = 1LL * ceil_div(W, bw) * ceil_div(H, bh) * ceil_div(T, bt);
-      // prefer wide boxes on ties (longer contiguous TMA rows)
-      if (best < 0 || cost < best) { best = cost; *BW = bw; *BH = bh; *BT = bt; }
+      if (best < 0 || cost < best) { best = cost; *BW = bw; *BH = bh; *BT = bt; }  // ties: widest box wins
     }
   }
 }
@@ -322,13 +394,18 @@ extern "C" int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream_) {
                  "conv_gemm: C2=%d must be a multiple of 64 and match a2", d->C2);
   MGLD_CHECK_ARG(d->taps == 1 || d->taps == 3 || d->taps == 9, "conv_gemm: taps=%d", d->taps);
   MGLD_CHECK_ARG(d->N > 0, "conv_gemm: N=%d", d->N);
-  const bool pair = d->epilogue == MGLD_EPI_GEGLU || d->epilogue == MGLD_EPI_SPADE;
   MGLD_CHECK_ARG(d->epilogue >= 0 && d->epilogue <= 2, "conv_gemm: epilogue=%d", d->epilogue);
-  if (pair) MGLD_CHECK_ARG(d->N % 128 == 0, "conv_gemm: pair epilogue needs N %% 128 == 0 (N=%d)", d->N);
+  const bool pair = d->epilogue == MGLD_EPI_GEGLU || d->epilogue == MGLD_EPI_SPADE;
+  if (pair)
+    MGLD_CHECK_ARG(d->N % 128 == 0 && !d->out_f32, "conv_gemm: pair epilogue needs N %% 128 == 0 (N=%d), fp16 out", d->N);
   if (d->epilogue == MGLD_EPI_SPADE)
     MGLD_CHECK_ARG(d->h && d->gn_stats && d->gn_weight && d->gn_bias && d->groups > 0 &&
                        (d->N / 2) % d->groups == 0,
                    "conv_gemm: SPADE epilogue operands missing");
+  MGLD_CHECK_ARG(d->ldout % 8 == 0 && d->out_col0 % 8 == 0 && (!d->res || d->ldres % 8 == 0) &&
+                     (!d->h || d->ldh % 8 == 0),
+                 "conv_gemm: leading dimensions / column offset must be multiples of 8");
+  MGLD_CHECK_ARG(!(d->out_f32 && d->res), "conv_gemm: residual with fp32 output is not supported");
 
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
@@ -337,71 +414,87 @@ extern "C" int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream_) {
   p.tiles_w = ceil_div(d->W, p.BW);
   p.tiles_h = ceil_div(d->H, p.BH);
   p.tiles_t = ceil_div(d->T, p.BT);
+  p.tiles_m = p.tiles_w * p.tiles_h * p.tiles_t;
   p.kchunks1 = ceil_div(d->C1, 64);
   p.kchunks = ceil_div(d->C1 + d->C2, 64);
   p.taps = d->taps;
   p.N = d->N;
-  p.block_n = pair ? 128 : (d->block_n > 0 ? d->block_n : pick_block_n(d->N));
-  MGLD_CHECK_ARG(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "conv_gemm: block_n=%d", p.block_n);
-  p.n_stage_cols = (d->epilogue == MGLD_EPI_GEGLU) ? 64 : p.block_n;
+  const int sms = num_sms();
+  p.block_n = pair ? 128 : (d->block_n > 0 ? d->block_n : pick_block_n(d->N, p.tiles_m, sms));
+  if (d->out_f32 && p.block_n > 128) p.block_n = 128;  // fp32 staging tile: 128 x 128 x 4 B = 64 KB
+  MGLD_CHECK_ARG(p.block_n % 32 == 0 && p.block_n >= 32 && p.block_n <= 256, "conv_gemm: block_n=%d", p.block_n);
+  p.tiles_n = ceil_div(d->N, p.block_n);
   p.n_out_tile = pair ? 64 : p.block_n;
   p.n_out_total = pair ? d->N / 2 : d->N;
   MGLD_CHECK_ARG(p.n_out_total % 8 == 0, "conv_gemm: output columns (%d) must be a multiple of 8", p.n_out_total);
+  p.panel_cols = (p.n_out_tile % 64 == 0) ? 64 : 32;
+  p.n_panels = d->out_f32 ? p.n_out_tile / 32 : p.n_out_tile / p.panel_cols;
+  p.acc_stride = p.block_n;  // multiple of 32 columns
   p.tmem_cols = 32;
-  while (p.tmem_cols < p.block_n) p.tmem_cols <<= 1;
+  while (p.tmem_cols < 2 * p.acc_stride) p.tmem_cols <<= 1;
   p.epilogue = d->epilogue; p.act = d->act; p.bias = d->bias;
   p.alpha = d->alpha; p.beta = d->beta;
-  p.res = reinterpret_cast<const __half*>(d->res); p.ldres = d->ldres;
-  p.h = reinterpret_cast<const __half*>(d->h); p.ldh = d->ldh;
+  p.has_res = d->res != nullptr; p.out_f32 = d->out_f32;
   p.gn_stats = d->gn_stats; p.gn_weight = d->gn_weight; p.gn_bias = d->gn_bias;
   p.groups = d->groups; p.ch_per_group = d->groups > 0 ? p.n_out_total / d->groups : 1;
-  p.out = d->out; p.ldout = d->ldout; p.out_col0 = d->out_col0; p.out_f32 = d->out_f32;
-  MGLD_CHECK_ARG(d->ldout % 8 == 0 && d->out_col0 % 8 == 0 && (!d->res || d->ldres % 8 == 0) &&
-                     (!d->h || d->ldh % 8 == 0),
-                 "conv_gemm: leading dimensions / column offset must be multiples of 8");
 
+  // shared memory plan: [A/B ring][staging panels][h panel (SPADE)][bias]
   const int stage_bytes = kABytes + p.block_n * 128;
-  int stages = (109 * 1024) / stage_bytes;                      // aim for two CTAs per SM
-  if (stages < 3) stages = (200 * 1024) / stage_bytes;          // otherwise one CTA with a deep pipeline
+  const int staging_bytes = d->out_f32 ? p.n_panels * kPanelBytes : p.n_out_tile * kBlockM * 2;
+  const int hstage_bytes = d->epilogue == MGLD_EPI_SPADE ? kPanelBytes : 0;
+  const int fixed = staging_bytes + hstage_bytes + 1024 /*bias*/ + 1024 /*alignment slack*/;
+  int stages = (224 * 1024 - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  MGLD_CHECK_ARG(stages >= 2, "conv_gemm: tile does not fit in shared memory (block_n=%d)", p.block_n);
   p.stages = stages;
-  const int staging_bytes = kBlockM * (p.n_stage_cols + 4) * 4;
-  int smem = stages * stage_bytes;
-  if (smem < staging_bytes) smem = staging_bytes;
-  smem += 1024;
+  p.off_staging = stages * stage_bytes;
+  p.off_hstage = p.off_staging + staging_bytes;
+  p.off_bias = p.off_hstage + hstage_bytes;
+  const int smem = p.off_bias + 1024 + 1024;
 
   // tensor maps
   const int lda = d->lda > 0 ? d->lda : d->C1;
   const int lda2 = d->lda2 > 0 ? d->lda2 : d->C2;
-  CUtensorMap tmA, tmA2, tmB;
+  CUtensorMap tmA, tmA2, tmB, tmOut, tmRes, tmH;
   {
-    uint64_t dims[4] = {(uint64_t)d->C1, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->T};
-    uint64_t str[3] = {(uint64_t)lda * 2, (uint64_t)lda * 2 * d->W, (uint64_t)lda * 2 * d->W * d->H};
-    uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, (uint32_t)p.BT};
-    int rc = make_tmap_f16(&tmA, d->a, 4, dims, str, box);
+    auto nhwc_map = [&](CUtensorMap* m, const void* base, int C, int ld, int box_cols = 64) {
+      uint32_t box[4] = {(uint32_t)box_cols, (uint32_t)p.BW, (uint32_t)p.BH, (uint32_t)p.BT};
+      uint64_t dims[4] = {(uint64_t)C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->T};
+      uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * d->W, (uint64_t)ld * 2 * d->W * d->H};
+      return make_tmap_f16(m, base, 4, dims, str, box);
+    };
+    int rc = nhwc_map(&tmA, d->a, d->C1, lda);
     if (rc) return rc;
-    if (d->a2) {
-      uint64_t dims2[4] = {(uint64_t)d->C2, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->T};
-      uint64_t str2[3] = {(uint64_t)lda2 * 2, (uint64_t)lda2 * 2 * d->W, (uint64_t)lda2 * 2 * d->W * d->H};
-      rc = make_tmap_f16(&tmA2, d->a2, 4, dims2, str2, box);
-      if (rc) return rc;
-    } else {
-      tmA2 = tmA;
-    }
+    if (d->a2) { rc = nhwc_map(&tmA2, d->a2, d->C2, lda2); if (rc) return rc; }
+    else tmA2 = tmA;
     const uint64_t K = (uint64_t)d->taps * (d->C1 + d->C2);
     uint64_t dimsB[2] = {K, (uint64_t)d->N};
     uint64_t strB[1] = {K * 2};
     uint32_t boxB[2] = {64, (uint32_t)p.block_n};
     rc = make_tmap_f16(&tmB, d->w, 2, dimsB, strB, boxB);
     if (rc) return rc;
+    if (d->out_f32) {
+      uint64_t dims[4] = {(uint64_t)p.n_out_total, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->T};
+      uint64_t str[3] = {(uint64_t)d->ldout * 4, (uint64_t)d->ldout * 4 * d->W, (uint64_t)d->ldout * 4 * d->W * d->H};
+      uint32_t box32[4] = {32, (uint32_t)p.BW, (uint32_t)p.BH, (uint32_t)p.BT};
+      rc = make_tmap_f32(&tmOut, reinterpret_cast<const float*>(d->out) + d->out_col0, 4, dims, str, box32);
+    } else {
+      rc = nhwc_map(&tmOut, reinterpret_cast<const __half*>(d->out) + d->out_col0, p.n_out_total, d->ldout, p.panel_cols);
+    }
+    if (rc) return rc;
+    if (d->res) { rc = nhwc_map(&tmRes, d->res, p.n_out_total, d->ldres, p.panel_cols); if (rc) return rc; }
+    else tmRes = tmA;
+    if (d->epilogue == MGLD_EPI_SPADE) { rc = nhwc_map(&tmH, d->h, p.n_out_total, d->ldh); if (rc) return rc; }
+    else tmH = tmA;
   }
 
   if (!g_attr_set) {
-    MGLD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    MGLD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     g_attr_set = true;
   }
-  dim3 grid(p.tiles_w * p.tiles_h * p.tiles_t, ceil_div(d->N, p.block_n), 1);
-  conv_gemm_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmA2, tmB, p);
+  const int total_tiles = p.tiles_m * p.tiles_n;
+  dim3 grid(total_tiles < sms ? total_tiles : sms, 1, 1);
+  conv_gemm_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmA2, tmB, tmOut, tmRes, tmH, p);
   MGLD_LAUNCH_CHECK("conv_gemm_kernel");
   return MGLD_OK;
 }

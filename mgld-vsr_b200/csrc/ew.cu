@@ -88,36 +88,43 @@ __global__ void im2col_s2_kernel(const uint4* __restrict__ in, uint4* __restrict
 // ---------------------------------------------------------------------------------------------------------------
 // direct conv with tiny Cin (<= 8): in (N,Cin,H,W) fp32 -> out NHWC fp16 [N,H,W,Cout] (+bias), k = 1 or 3 (pad k/2)
 // ---------------------------------------------------------------------------------------------------------------
+// blockIdx.y selects a chunk of 128 output channels (thread == channel, its <=72 weights live in registers);
+// blockIdx.x a batch of 32 pixels whose input patches are staged once in shared memory and reused by all channels.
+constexpr int kScPix = 32;
 __global__ void conv_small_cin_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                       const float* __restrict__ bias, __half* __restrict__ out, int N, int Cin, int H,
                                       int W, int Cout, int ks, int ldo) {
-  extern __shared__ float sw[];  // [Cout][Cin*ks*ks] + bias
-  const int K = Cin * ks * ks;
-  for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[Cout * K + i] = bias ? bias[i] : 0.f;
-  __syncthreads();
-  const int pix_per_block = 16;
-  const long long p0 = static_cast<long long>(blockIdx.x) * pix_per_block;
+  __shared__ float patch[kScPix][73];
+  const int K = Cin * ks * ks, pad = ks / 2;
   const long long total = static_cast<long long>(N) * H * W;
-  const int pad = ks / 2;
-  for (int pp = 0; pp < pix_per_block; ++pp) {
+  const long long p0 = static_cast<long long>(blockIdx.x) * kScPix;
+  const int co = blockIdx.y * 128 + threadIdx.x;
+  for (int i = threadIdx.x; i < kScPix * K; i += blockDim.x) {
+    const int pp = i / K, k = i - pp * K;
+    const long long p = p0 + pp;
+    float v = 0.f;
+    if (p < total) {
+      const int x = p % W, y = (p / W) % H, n = p / (static_cast<long long>(W) * H);
+      const int c = k / (ks * ks), ky = (k / ks) % ks, kx = k % ks;
+      const int iy = y + ky - pad, ix = x + kx - pad;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(in + ((static_cast<long long>(n) * Cin + c) * H + iy) * W + ix);
+    }
+    patch[pp][k] = v;
+  }
+  __syncthreads();
+  if (co >= Cout) return;
+  float wr[72];
+#pragma unroll
+  for (int k = 0; k < 72; ++k) wr[k] = k < K ? __ldg(w + static_cast<long long>(co) * K + k) : 0.f;
+  const float b = bias ? __ldg(bias + co) : 0.f;
+  for (int pp = 0; pp < kScPix; ++pp) {
     const long long p = p0 + pp;
     if (p >= total) break;
-    const int x = p % W, y = (p / W) % H, n = p / (static_cast<long long>(W) * H);
-    float patch[72];
-    for (int c = 0; c < Cin; ++c)
-      for (int ky = 0; ky < ks; ++ky)
-        for (int kx = 0; kx < ks; ++kx) {
-          const int iy = y + ky - pad, ix = x + kx - pad;
-          patch[(c * ks + ky) * ks + kx] =
-              (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(in + ((static_cast<long long>(n) * Cin + c) * H + iy) * W + ix) : 0.f;
-        }
-    for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
-      float acc = sw[Cout * K + co];
-      const float* wr = sw + co * K;
-      for (int k = 0; k < K; ++k) acc = fmaf(patch[k], wr[k], acc);
-      out[p * ldo + co] = __float2half_rn(acc);
-    }
+    float acc = b;
+#pragma unroll
+    for (int k = 0; k < 72; ++k)
+      if (k < K) acc = fmaf(patch[pp][k], wr[k], acc);
+    out[p * ldo + co] = __float2half_rn(acc);
   }
 }
 
@@ -364,11 +371,9 @@ extern "C" int mgld_im2col_s2_f16(const void* in, void* out, int t, int h, int w
 extern "C" int mgld_conv_small_cin_f32(const float* in, const float* w, const float* bias, void* out, int n, int cin,
                                        int h, int wd, int cout, int ks, int ldo, void* stream) {
   MGLD_CHECK_ARG(in && w && out && cin > 0 && cin <= 8 && (ks == 1 || ks == 3) && cout > 0, "conv_small_cin: bad arguments");
-  const int K = cin * ks * ks;
-  const size_t smem = (size_t)(cout * K + cout) * sizeof(float);
-  MGLD_CHECK_ARG(smem <= 48 * 1024, "conv_small_cin: weights do not fit in shared memory");
   const long long total = 1LL * n * h * wd;
-  conv_small_cin_kernel<<<(int)((total + 15) / 16), 128, smem, (cudaStream_t)stream>>>(in, w, bias, (__half*)out, n, cin, h, wd, cout, ks, ldo > 0 ? ldo : cout);
+  dim3 grid((unsigned)((total + kScPix - 1) / kScPix), (unsigned)ceil_div(cout, 128));
+  conv_small_cin_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(in, w, bias, (__half*)out, n, cin, h, wd, cout, ks, ldo > 0 ? ldo : cout);
   MGLD_LAUNCH_CHECK("conv_small_cin_kernel");
   return MGLD_OK;
 }

@@ -37,6 +37,7 @@ __device__ __forceinline__ uint4 load_cat8(const __half* x1, int C1, int ld1, co
 }
 
 constexpr int kGnRowsPerBlock = 64;
+constexpr int kGnApplyItems = 1024;  // 8-channel vectors per block in gn_apply
 
 // sums[t][g] += (sum, sumsq) over rows [r0, r0+64) of frame t.  Double accumulation across blocks.
 __global__ void gn_stats_kernel(const __half* __restrict__ x1, int C1, int ld1, const __half* __restrict__ x2, int C2,
@@ -105,11 +106,15 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, int ld1, 
     sh[2 * g + 1] = (float)(1.0 / sqrt(var + eps));
   }
   __syncthreads();
-  const int r0 = blockIdx.x * kGnRowsPerBlock;
-  const int rows = min(kGnRowsPerBlock, HW - r0);
-  for (int idx = threadIdx.x; idx < rows * vpr; idx += blockDim.x) {
-    const int r = idx / vpr, v = idx - r * vpr;
-    const long long m = static_cast<long long>(t) * HW + r0 + r;
+  // each block covers kGnApplyItems consecutive 8-channel vectors of frame t; 4 independent loads in flight per thread
+  const long long base = static_cast<long long>(blockIdx.x) * kGnApplyItems;
+  const long long total = static_cast<long long>(HW) * vpr;
+#pragma unroll
+  for (int j = 0; j < kGnApplyItems / 256; ++j) {
+    const long long idx = base + j * 256 + threadIdx.x;
+    if (idx >= total) break;
+    const int r = idx / vpr, v = idx - static_cast<long long>(r) * vpr;
+    const long long m = static_cast<long long>(t) * HW + r;
     float f[8];
     unpack8(load_cat8(x1, C1, ld1, x2, ld2, m, v * 8), f);
 #pragma unroll
@@ -232,7 +237,7 @@ extern "C" int mgld_gn_apply_f16(const void* x1, int C1, int ld1, const void* x2
   MGLD_CHECK_ARG(x1 && sums && out && T > 0 && HW > 0 && groups > 0, "gn_apply: bad arguments");
   MGLD_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0 && C % groups == 0, "gn_apply: C1=%d C2=%d G=%d", C1, C2, groups);
   MGLD_CHECK_ARG((gamma != nullptr) == (beta != nullptr), "gn_apply: gamma/beta");
-  dim3 grid(ceil_div(HW, kGnRowsPerBlock), T);
+  dim3 grid((unsigned)((static_cast<long long>(HW) * (C / 8) + kGnApplyItems - 1) / kGnApplyItems), T);
   gn_apply_kernel<<<grid, 256, 2 * groups * sizeof(float), (cudaStream_t)stream>>>(
       (const __half*)x1, C1, ld1 > 0 ? ld1 : C1, (const __half*)x2, C2, ld2 > 0 ? ld2 : C2, HW, groups, sums, eps,
       gamma, beta, silu, (__half*)out, ldo > 0 ? ldo : C);

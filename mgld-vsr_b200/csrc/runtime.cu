@@ -63,6 +63,25 @@ int make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint64_t* di
   return MGLD_OK;
 }
 
+int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+  if (!g_encode) {
+    set_error("mgld_init() has not been called");
+    return MGLD_ERR_NOT_INIT;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  if (box[0] != 32) { set_error("make_tmap_f32: inner box must be 32 elements"); return MGLD_ERR_ARG; }
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(f32) failed (%d)", (int)r); return MGLD_ERR_CUDA; }
+  return MGLD_OK;
+}
+
 }  // namespace mgld
 
 using namespace mgld;

@@ -188,7 +188,7 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
     def register_schedule(self, given_betas=None, beta_schedule="linear", timesteps=1000, linear_start=1e-4,
                           linear_end=2e-2, cosine_s=8e-3):
         if given_betas is not None:
-            betas = np.asarray(given_betas, dtype=np.float64)
+            betas = np.asarray(given_betas)   # dtype kept: the script passes float32 (script :324-326)
         else:
             betas = make_beta_schedule(beta_schedule, timesteps, linear_start, linear_end, cosine_s)
         alphas = 1.0 - betas
@@ -287,11 +287,11 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
         """ddpm.py:4601-4616 (float64; x midpoint (w-1)/2 but y midpoint h/2 — reproduced as is)."""
         var = 0.01
         midpoint = (tile_width - 1) / 2
-        x_probs = [math.exp(-(x - midpoint) * (x - midpoint) / (tile_width * tile_width) / (2 * var)) /
-                   math.sqrt(2 * math.pi * var) for x in range(tile_width)]
+        x_probs = [np.exp(-(x - midpoint) * (x - midpoint) / (tile_width * tile_width) / (2 * var)) /
+                   np.sqrt(2 * np.pi * var) for x in range(tile_width)]
         midpoint = tile_height / 2
-        y_probs = [math.exp(-(y - midpoint) * (y - midpoint) / (tile_height * tile_height) / (2 * var)) /
-                   math.sqrt(2 * math.pi * var) for y in range(tile_height)]
+        y_probs = [np.exp(-(y - midpoint) * (y - midpoint) / (tile_height * tile_height) / (2 * var)) /
+                   np.sqrt(2 * np.pi * var) for y in range(tile_height)]
         weights = np.outer(y_probs, x_probs)
         ch = self.channels if self.configs is None else self.configs.model.params.channels
         return torch.tile(torch.tensor(weights, device=self.device), (nbatches, ch, 1, 1))

@@ -417,7 +417,7 @@ def make_beta_schedule_linear(n_timestep, linear_start, linear_end):
 
 def schedule_tables(betas):
     """DDPM.register_schedule, ddpm.py:237-277 (v_posterior = 0, eps-parameterisation)."""
-    betas = np.asarray(betas, dtype=np.float64)
+    betas = np.asarray(betas)   # NOT cast: the script passes float32 betas and numpy then computes the tables in float32
     alphas = 1.0 - betas
     ac = np.cumprod(alphas, axis=0)
     ac_prev = np.append(1.0, ac[:-1])
@@ -463,7 +463,7 @@ def respaced_schedule(linear_start=0.00085, linear_end=0.0120, timesteps=1000, d
         if i in use:
             new_betas.append(1 - ac / last)
             last = ac
-    new_betas = np.array([float(b) for b in new_betas])
+    new_betas = np.array([b.data.cpu().numpy() for b in new_betas])   # float32, exactly as script :324
     return base, schedule_tables(new_betas), sorted(use)
 
 

@@ -129,10 +129,13 @@ def test_schedule_tables_bitwise_vs_reference():
 def test_gaussian_weights_and_tiles_vs_reference():
     dd = _ref("ldm.models.diffusion.ddpm")
     from mgld_vsr_b200.config import _wrap
-    stub = type("S", (), {"device": "cpu", "configs": _wrap({"model": {"params": {"channels": 4}}})})()
+    stub = type("S", (), {"betas": torch.zeros(1), "configs": _wrap({"model": {"params": {"channels": 4}}})})()
     for ts in (32, 64):
         assert torch.equal(dd.LatentDiffusionVSRTextWT._gaussian_weights(stub, ts, ts, 1), R.gaussian_weights(ts, ts, 1))
     from mgld_vsr_b200.ddpm import LatentDiffusionVSRTextWT as P
+    prod = P.__new__(P)
+    prod.device, prod.configs, prod.channels = torch.device("cpu"), None, 4
+    assert torch.equal(prod._gaussian_weights(64, 64, 1), R.gaussian_weights(64, 64, 1))
     for (h, w) in [(64, 64), (92, 120), (120, 120), (136, 240), (65, 64)]:
         assert P._tile_offsets(h, w, 64, 32) == R.canvas_tiles(h, w, 64, 32)
     assert len(R.canvas_tiles(120, 120, 64, 32)) == 9 and len(R.canvas_tiles(92, 120, 64, 32)) == 6

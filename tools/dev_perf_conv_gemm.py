@@ -22,7 +22,7 @@ for (T, H, W, Ci, Co, taps) in shapes:
     x = torch.randn(T, H, W, Ci, device=dev).half(); w = (torch.randn(Co, taps * Ci, device=dev) * 0.02).half()
     b = torch.randn(Co, device=dev)
     out = torch.empty(T, H, W, Co, device=dev, dtype=torch.float16)
-    for bn in ([0, 128, 256] if Co % 256 == 0 else [0, 128] if Co % 128 == 0 else [0, 64]):
+    for bn in ([0, 128, 256] if Co % 256 == 0 else [0, 128] if Co % 128 == 0 else [0, 64, 160] if Co % 160 == 0 else [0, 64]):
         ms = bench(lambda: ops.conv_gemm(x, w, taps=taps, bias=b, out=out, block_n=bn))
         fl = 2.0 * T * H * W * Ci * Co * taps
         print(f"T{T} {H}x{W} {Ci}->{Co} taps{taps} bn{bn}: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s", flush=True)
