@@ -182,7 +182,7 @@ def test_stem_and_head_convs():
 def test_time_embedding_gemv_temporal_attention_gaussian():
     O = ops()
     t = torch.tensor([937.0], device=DEV)
-    assert rel_err(O.timestep_embedding(t, 320), E.timestep_embedding(t.cpu(), 320).to(DEV)) < 1e-5
+    assert rel_err(O.timestep_embedding(t, 320), E.timestep_embedding(t.cpu(), 320).to(DEV)) < 2e-4   # fp32 sin/cos of ~1e3 rad
     x, w, b, a = rnd(1280), rnd(640, 1280, scale=0.03).half(), rnd(640), rnd(640, seed=3)
     assert rel_err(O.gemv(x, w, b, a, True, False), E.gemv(x, w, b, a, True, False)) < 1e-4
     assert rel_err(O.gemv(x, w, b, None, False, True), E.gemv(x, w, b, None, False, True)) < 1e-4
