@@ -119,12 +119,14 @@ class _EpsRunner:
                     self._eager(sx, ssc, st, context)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
+            n0 = self.m.ops.LAUNCHES[0]
             with torch.cuda.graph(graph):
                 out = self._eager(sx, ssc, st, context)
-            g = self.graphs[key] = (graph, sx, ssc, st, out)
-        graph, sx, ssc, st, out = g
+            g = self.graphs[key] = (graph, sx, ssc, st, out, self.m.ops.LAUNCHES[0] - n0)
+        graph, sx, ssc, st, out, n_kernels = g
         sx.copy_(x); ssc.copy_(sc); st.copy_(t)
         graph.replay()
+        self.m.ops.LAUNCHES[0] += n_kernels          # kernels replayed by the graph
         return out.clone()
 
 

@@ -8,6 +8,15 @@ import torch
 
 from . import lib as _L
 
+# number of mgld kernels launched through this module (bench.py reports it as `gpu_launches`; launches replayed from a
+# CUDA graph are added by the graph owner: ddpm._EpsRunner)
+LAUNCHES = [0]
+
+
+def _count(n=1):
+    LAUNCHES[0] += n
+
+
 TAPS_1, TAPS_T3, TAPS_3X3 = 1, 3, 9
 EPI_LINEAR, EPI_GEGLU, EPI_SPADE = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_LRELU02, ACT_GELU = 0, 1, 2, 3, 4
@@ -87,6 +96,7 @@ def conv_gemm(a, w, *, taps=TAPS_1, a2=None, bias=None, epilogue=EPI_LINEAR, act
     d.gn_bias = gn_bias.data_ptr() if gn_bias is not None else None
     d.groups = groups
     d.out, d.ldout, d.out_col0, d.out_f32 = out.data_ptr(), ldout, out_col0, int(out_f32)
+    _count(1)
     _L.check(_L.lib().mgld_conv_gemm(ctypes.byref(d), _L.stream_ptr()))
     return out
 
@@ -111,6 +121,7 @@ def attention(q, k, v, *, batch, heads, head_dim, nq, nkv, scale, q_col0=0, k_co
     d.batch, d.heads, d.head_dim, d.nq, d.nkv = batch, heads, head_dim, nq, nkv
     d.kv_batched, d.scale = int(kv_batched), float(scale)
     d.out, d.ldo = out.data_ptr(), out.stride(0)
+    _count(1)
     _L.check(_L.lib().mgld_attention(ctypes.byref(d), _L.stream_ptr()))
     return out
 
@@ -127,6 +138,7 @@ def flow_warp_f32(x, flow, flow_layout=0, nearest=False, border=False, align_cor
     x, flow = _f32c(x), _f32c(flow)
     n, c, h, w = x.shape
     out = torch.empty_like(x)
+    _count(1)
     _L.check(_L.lib().mgld_flow_warp_f32(_L.ptr(x), _L.ptr(flow), _L.ptr(out), n, c, h, w, int(flow_layout),
                                          int(nearest), int(border), int(align_corners), _L.stream_ptr()))
     return out
@@ -136,6 +148,7 @@ def flow_warp_bwd_input_f32(grad_out, flow, flow_layout=0, border=False, align_c
     grad_out, flow = _f32c(grad_out), _f32c(flow)
     n, c, h, w = grad_out.shape
     gin = torch.empty_like(grad_out)
+    _count(1)
     _L.check(_L.lib().mgld_flow_warp_bwd_input_f32(_L.ptr(grad_out), _L.ptr(flow), _L.ptr(gin), n, c, h, w,
                                                    int(flow_layout), int(border), int(align_corners),
                                                    _L.stream_ptr()))
@@ -147,6 +160,7 @@ def fb_consistency_f32(fwd_flow, bwd_flow, alpha=0.01, beta=0.5):
     b, _, h, w = fwd_flow.shape
     fo = torch.empty(b, h, w, device=fwd_flow.device, dtype=torch.float32)
     bo = torch.empty_like(fo)
+    _count(1)
     _L.check(_L.lib().mgld_fb_consistency_f32(_L.ptr(fwd_flow), _L.ptr(bwd_flow), _L.ptr(fo), _L.ptr(bo), b, h, w,
                                               ctypes.c_float(alpha), ctypes.c_float(beta), _L.stream_ptr()))
     return fo, bo
@@ -160,6 +174,7 @@ def motion_guidance_f32(latents, flow_fwd_prop, flow_bwd_prop, fwd_occ, bwd_occ,
     out = torch.empty_like(latents)
     loss = torch.empty(1, device=latents.device, dtype=torch.float32) if want_loss else None
     args = [_f32c(a) if a is not None else None for a in (flow_fwd_prop, flow_bwd_prop, fwd_occ, bwd_occ)]
+    _count(2)
     _L.check(_L.lib().mgld_motion_guidance_f32(_L.ptr(latents), _L.ptr(args[0]), _L.ptr(args[1]), _L.ptr(args[2]),
                                                _L.ptr(args[3]), _L.ptr(ws), _L.ptr(out), _L.ptr(loss),
                                                ctypes.c_float(step), t, c, h, w, _L.stream_ptr()))
@@ -170,6 +185,7 @@ def resize_flow_f32(flow, oh, ow):
     flow = _f32c(flow)
     n, _, h, w = flow.shape
     out = torch.empty(n, 2, oh, ow, device=flow.device, dtype=torch.float32)
+    _count(1)
     _L.check(_L.lib().mgld_resize_flow_f32(_L.ptr(flow), _L.ptr(out), n, h, w, oh, ow, _L.stream_ptr()))
     return out
 
@@ -190,6 +206,7 @@ def canvas_posterior_f32(x, eps_tiles, tile_w, noise, offsets, tile_size, c_reci
     noise = _f32c(noise) if noise is not None else None
     assert tile_w.dtype == torch.float64 and tile_w.is_cuda
     tile_w = tile_w.contiguous()
+    _count(1)
     _L.check(_L.lib().mgld_canvas_posterior_f32(
         _L.ptr(x), _L.ptr(ptrs), _L.ptr(tile_w), _L.ptr(noise), _L.ptr(out), _L.ptr(eps_out), n, ox, oy, T * C, h, w,
         tile_size, ctypes.c_float(c_recip), ctypes.c_float(c_recipm1), ctypes.c_float(c1), ctypes.c_float(c2),
@@ -217,6 +234,7 @@ def gn_stats(x1, x2=None, groups=32):
     T, HW, C1, ld1 = _thwc(x1)
     C2, ld2 = (x2.shape[-1], x2.stride(-2)) if x2 is not None else (0, 0)
     sums = torch.zeros(T, groups, 2, device=x1.device, dtype=torch.float64)
+    _count(1)
     _L.check(_L.lib().mgld_gn_stats_f16(_L.ptr(x1), C1, ld1, _L.ptr(x2), C2, ld2, T, HW, groups, _L.ptr(sums),
                                         _L.stream_ptr()))
     return sums
@@ -225,6 +243,7 @@ def gn_stats(x1, x2=None, groups=32):
 def gn_finalize(sums, HW, C, eps):
     T, G = sums.shape[:2]
     stats = torch.empty(T, G, 2, device=sums.device, dtype=torch.float32)
+    _count(1)
     _L.check(_L.lib().mgld_gn_finalize(_L.ptr(sums), _L.ptr(stats), T, G, HW, C, ctypes.c_double(eps), _L.stream_ptr()))
     return stats
 
@@ -233,6 +252,7 @@ def gn_apply(x1, sums, eps, gamma, beta, silu, x2=None, groups=32):
     T, HW, C1, ld1 = _thwc(x1)
     C2, ld2 = (x2.shape[-1], x2.stride(-2)) if x2 is not None else (0, 0)
     out = torch.empty(*x1.shape[:-1], C1 + C2, device=x1.device, dtype=torch.float16)
+    _count(1)
     _L.check(_L.lib().mgld_gn_apply_f16(_L.ptr(x1), C1, ld1, _L.ptr(x2), C2, ld2, T, HW, groups, _L.ptr(sums),
                                         ctypes.c_double(eps), _L.ptr(gamma), _L.ptr(beta), int(silu), _L.ptr(out),
                                         C1 + C2, _L.stream_ptr()))
@@ -245,6 +265,7 @@ def layernorm(x, gamma, beta, eps=1e-5):
     M = x.numel() // C
     assert x.is_contiguous()
     out = torch.empty_like(x)
+    _count(1)
     _L.check(_L.lib().mgld_layernorm_f16(_L.ptr(x), C, M, C, _L.ptr(gamma), _L.ptr(beta), ctypes.c_float(eps),
                                          _L.ptr(out), C, _L.stream_ptr()))
     return out
@@ -256,6 +277,7 @@ def softmax_rows(s, scale, ldp=None):
     ldp = n if ldp is None else ldp
     p = torch.zeros(rows, ldp, device=s.device, dtype=torch.float16) if ldp != n else \
         torch.empty(rows, n, device=s.device, dtype=torch.float16)
+    _count(1)
     _L.check(_L.lib().mgld_softmax_rows_f32(_L.ptr(s), ctypes.c_longlong(s.stride(0)), rows, n, ctypes.c_float(scale),
                                             _L.ptr(p), ctypes.c_longlong(ldp), _L.stream_ptr()))
     return p
@@ -268,6 +290,7 @@ def nchw_to_nhwc(x, scale=1.0):
     x = _f32c(x)
     n, c, h, w = x.shape
     out = torch.empty(n, h, w, c, device=x.device, dtype=torch.float16)
+    _count(1)
     _L.check(_L.lib().mgld_nchw_f32_to_nhwc_f16(_L.ptr(x), _L.ptr(out), n, c, h, w, c, ctypes.c_float(scale),
                                                 _L.stream_ptr()))
     return out
@@ -277,6 +300,7 @@ def nhwc_to_nchw(x, scale=1.0):
     assert x.dtype == torch.float16 and x.is_contiguous()
     n, h, w, c = x.shape
     out = torch.empty(n, c, h, w, device=x.device, dtype=torch.float32)
+    _count(1)
     _L.check(_L.lib().mgld_nhwc_f16_to_nchw_f32(_L.ptr(x), _L.ptr(out), n, c, h, w, c, ctypes.c_float(scale),
                                                 _L.stream_ptr()))
     return out
@@ -286,6 +310,7 @@ def upsample2x(x):
     assert x.dtype == torch.float16 and x.is_contiguous()
     t, h, w, c = x.shape
     out = torch.empty(t, 2 * h, 2 * w, c, device=x.device, dtype=torch.float16)
+    _count(1)
     _L.check(_L.lib().mgld_upsample_nearest2x_f16(_L.ptr(x), _L.ptr(out), t, h, w, c, _L.stream_ptr()))
     return out
 
@@ -297,6 +322,7 @@ def im2col_s2(x, pad):
     ho = (h + 2 * pad - 3) // 2 + 1 if pad == 1 else (h + 1 - 3) // 2 + 1
     wo = (w + 2 * pad - 3) // 2 + 1 if pad == 1 else (w + 1 - 3) // 2 + 1
     out = torch.empty(t, ho, wo, 9 * c, device=x.device, dtype=torch.float16)
+    _count(1)
     _L.check(_L.lib().mgld_im2col_s2_f16(_L.ptr(x), _L.ptr(out), t, h, w, c, ho, wo, pad, _L.stream_ptr()))
     return out
 
@@ -307,6 +333,7 @@ def conv_small_cin(x, w, bias):
     n, cin, h, wd = x.shape
     cout, _, ks, _ = w.shape
     out = torch.empty(n, h, wd, cout, device=x.device, dtype=torch.float16)
+    _count(1)
     _L.check(_L.lib().mgld_conv_small_cin_f32(_L.ptr(x), _L.ptr(w), _L.ptr(bias), _L.ptr(out), n, cin, h, wd, cout, ks,
                                               cout, _L.stream_ptr()))
     return out
@@ -317,6 +344,7 @@ def conv_small_f32(x, w, bias):
     n, cin, h, wd = x.shape
     cout, _, ks, _ = w.shape
     out = torch.empty(n, cout, h, wd, device=x.device, dtype=torch.float32)
+    _count(1)
     _L.check(_L.lib().mgld_conv_small_f32(_L.ptr(x), _L.ptr(w), _L.ptr(bias), _L.ptr(out), n, cin, h, wd, cout, ks,
                                           _L.stream_ptr()))
     return out
@@ -328,6 +356,7 @@ def conv3x3_small_cout(x, w_packed, bias):
     n, h, wd, c = x.shape
     cout = w_packed.shape[0]
     out = torch.empty(n, cout, h, wd, device=x.device, dtype=torch.float32)
+    _count(1)
     _L.check(_L.lib().mgld_conv3x3_small_cout_f16(_L.ptr(x), _L.ptr(w_packed), _L.ptr(bias), _L.ptr(out), n, h, wd, c,
                                                   cout, c, _L.stream_ptr()))
     return out
@@ -337,6 +366,7 @@ def gemv(x, w, bias=None, add=None, silu_in=False, silu_out=False):
     """x fp32 [K], w fp16 [N,K] -> fp32 [N]"""
     n, k = w.shape
     y = torch.empty(n, device=w.device, dtype=torch.float32)
+    _count(1)
     _L.check(_L.lib().mgld_gemv_f32(_L.ptr(x), _L.ptr(w), _L.ptr(bias), _L.ptr(add), _L.ptr(y), n, k, int(silu_in),
                                     int(silu_out), _L.stream_ptr()))
     return y
@@ -346,6 +376,7 @@ def timestep_embedding(t, dim, max_period=10000.0):
     """t: CUDA fp32 tensor with one element (read on the device, so the launch is graph-replayable)."""
     assert t.is_cuda and t.dtype == torch.float32 and t.numel() == 1
     out = torch.empty(dim, device=t.device, dtype=torch.float32)
+    _count(1)
     _L.check(_L.lib().mgld_timestep_embedding_f32(_L.ptr(t), _L.ptr(out), dim,
                                                   ctypes.c_float(max_period), _L.stream_ptr()))
     return out
@@ -357,6 +388,7 @@ def temporal_attention(qkv, heads, scale):
     t, hw, c3 = qkv.shape
     c = c3 // 3
     out = torch.empty(t, hw, c, device=qkv.device, dtype=torch.float16)
+    _count(1)
     _L.check(_L.lib().mgld_temporal_attention_f16(_L.ptr(qkv), _L.ptr(out), t, hw, c, heads, ctypes.c_float(scale),
                                                   _L.stream_ptr()))
     return out
@@ -367,6 +399,7 @@ def gaussian_sample(moments, noise, scale):
     n, c2, h, w = moments.shape
     out = torch.empty(n, c2 // 2, h, w, device=moments.device, dtype=torch.float32)
     noise = _f32c(noise) if noise is not None else None
+    _count(1)
     _L.check(_L.lib().mgld_gaussian_sample_f32(_L.ptr(moments), _L.ptr(noise), _L.ptr(out), n, c2 // 2, h, w,
                                                ctypes.c_float(scale), _L.stream_ptr()))
     return out
@@ -375,6 +408,7 @@ def gaussian_sample(moments, noise, scale):
 def axpby(x, y, a, b):
     assert x.dtype == torch.float16 and x.is_contiguous() and y.is_contiguous() and x.shape == y.shape
     out = torch.empty_like(x)
+    _count(1)
     _L.check(_L.lib().mgld_axpby_f16(_L.ptr(x), _L.ptr(y), _L.ptr(out), ctypes.c_float(a), ctypes.c_float(b),
                                      ctypes.c_longlong(x.numel()), _L.stream_ptr()))
     return out

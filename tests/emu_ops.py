@@ -9,6 +9,7 @@ import math
 import torch
 import torch.nn.functional as F
 
+LAUNCHES = [0]
 TAPS_1, TAPS_T3, TAPS_3X3 = 1, 3, 9
 EPI_LINEAR, EPI_GEGLU, EPI_SPADE = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_LRELU02, ACT_GELU = 0, 1, 2, 3, 4
