@@ -246,7 +246,7 @@ def main():
     clip_host = synthetic_clip(42 + rank).pin_memory()
     flows = [(a.to(dev), b.to(dev)) for a, b in synthetic_flows(7 + rank, n_seg, T, 64, 64)]
     out_host = torch.empty(N_FRAMES_CLIP, 3, 512, 512).pin_memory()
-    gather_buf = torch.empty(world, N_FRAMES_CLIP, 3, 512, 512, dtype=torch.uint8, device=dev) if world > 1 else None
+    gather_buf = torch.empty(world * N_FRAMES_CLIP, 3, 512, 512, dtype=torch.uint8, device=dev) if world > 1 else None
 
     def run_clip(clip_dev):
         sr = pipe(clip_dev, context=context, flows_override=flows)

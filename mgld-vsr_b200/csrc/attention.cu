@@ -13,6 +13,7 @@
 // Replaces xformers.ops.memory_efficient_attention at ldm/modules/attention.py:298 (self), :371 (cross, K/V
 // batch-broadcast as :336-337) and QKVAttentionLegacy at ldm/modules/diffusionmodules/openaimodel.py:554-590.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/mgld.h"
@@ -285,6 +286,252 @@ static int launch_attention(const mgld_attention_desc* d, cudaStream_t stream) {
   return MGLD_OK;
 }
 
+
+// =====================================================================================================================
+// v2 (head_dim 64): two 128-row query tiles per CTA in ping-pong.  While softmax warpgroup i works on S_i(j), the tensor
+// core runs PV_{1-i}(j) and S_{1-i}(j+1).  P is written back to TMEM over the S columns (fp16, two per 32-bit column) and
+// consumed as the A operand of the PV MMA straight from TMEM (tcgen05.mma A-from-TMEM form) — no shared-memory round trip,
+// no proxy fence.  The O rescale is lazy: the running max is only advanced when it grew by more than 2^8 (in the exp2
+// domain), which keeps fp16 P <= 256 * row-max-probability and makes the rescale rare; the final O / l is exact for any
+// reference max.  One CTA per SM: 320 threads = TMA warp, MMA warp, 2 x 4 softmax warps; TMEM: S0 S1 (128 cols each),
+// O0 O1 (64 each) of the 512 columns; smem: Q 32 KB + 3 x (K,V) 32 KB.
+// =====================================================================================================================
+constexpr int kV2Threads = 320;
+constexpr int kV2Stages = 3;
+
+__global__ void __launch_bounds__(kV2Threads, 1)
+attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  constexpr int DH = 64;
+  constexpr int kTileBytes = 128 * DH * 2;  // 16 KB: one [128 x 64] fp16 operand tile
+  constexpr uint32_t kSCol0 = 0, kSCol1 = 128, kOCol0 = 256, kOCol1 = 320;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t q_full, kv_full[kV2Stages], kv_empty[kV2Stages], s_full[2], p_full[2], o_full;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem_base;                       // two tiles
+  const uint32_t sKV = sQ + 2 * kTileBytes;            // stage s: K at +s*2*kTileBytes, V after K
+
+  const int q0 = blockIdx.x * 256;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int nblk = (p.nkv + kKVTile - 1) / kKVTile;
+  const int kvb = p.kv_batched ? b : 0;
+  const bool tile1_live = q0 + 128 < p.nq;             // the second tile may be entirely out of range
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(smem_u32(&q_full), 1);
+    for (int s = 0; s < kV2Stages; ++s) { mbar_init(smem_u32(&kv_full[s]), 1); mbar_init(smem_u32(&kv_empty[s]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&p_full[i]), 128); }
+    mbar_init(smem_u32(&o_full), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(smem_u32(&q_full), 2 * kTileBytes);
+      tma_load_3d(sQ, &tmQ, smem_u32(&q_full), p.q_col0 + head * p.q_hstride, q0, b);
+      tma_load_3d(sQ + kTileBytes, &tmQ, smem_u32(&q_full), p.q_col0 + head * p.q_hstride, q0 + 128, b);
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j % kV2Stages;
+        mbar_wait(smem_u32(&kv_empty[s]), ((j / kV2Stages) & 1) ^ 1);
+        const uint32_t fb = smem_u32(&kv_full[s]);
+        mbar_expect_tx(fb, 2 * kTileBytes);
+        tma_load_3d(sKV + s * 2 * kTileBytes, &tmK, fb, p.k_col0 + head * p.k_hstride, j * kKVTile, kvb);
+        tma_load_3d(sKV + s * 2 * kTileBytes + kTileBytes, &tmV, fb, p.v_col0 + head * p.v_hstride, j * kKVTile, kvb);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_f16(128, kKVTile, 0, 0);
+      const uint32_t idesc_o = umma_idesc_f16(128, DH, 0, 1);  // B = V, MN-major
+      auto issue_s = [&](int i, int j) {
+        const uint32_t sk = sKV + (j % kV2Stages) * 2 * kTileBytes;
+        const uint32_t sq = sQ + i * kTileBytes;
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          umma_ss(tmem_base + (i ? kSCol1 : kSCol0), umma_smem_desc(sq + k * 32, 0, 1024, kSwz128),
+                  umma_smem_desc(sk + k * 32, 0, 1024, kSwz128), idesc_s, k != 0);
+        umma_commit(smem_u32(&s_full[i]));
+      };
+      mbar_wait(smem_u32(&q_full), 0);
+      mbar_wait(smem_u32(&kv_full[0]), 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j % kV2Stages;
+        const uint32_t sv = sKV + s * 2 * kTileBytes + kTileBytes;
+        if (j + 1 < nblk) {  // K_{j+1} must have landed before S_i(j+1) is issued below
+          mbar_wait(smem_u32(&kv_full[(j + 1) % kV2Stages]), ((j + 1) / kV2Stages) & 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+          mbar_wait(smem_u32(&p_full[i]), j & 1);
+          tc_fence_after();
+          const uint32_t pcol = tmem_base + (i ? kSCol1 : kSCol0);
+          const uint32_t ocol = tmem_base + (i ? kOCol1 : kOCol0);
+#pragma unroll
+          for (int k = 0; k < kKVTile / 16; ++k)  // A: 16 keys = 8 packed columns per step; B: 16 key rows = 2048 B
+            umma_ts(ocol, pcol + k * 8, umma_smem_desc(sv + k * 2048, 0, 1024, kSwz128), idesc_o, (j | k) != 0);
+          if (i == 1) umma_commit(smem_u32(&kv_empty[s]));
+          if (j + 1 < nblk) issue_s(i, j + 1);
+        }
+      }
+      umma_commit(smem_u32(&o_full));
+    }
+  } else {
+    // softmax warpgroup i: warps 2-5 -> tile 0, warps 6-9 -> tile 1; thread == query row
+    const int i = (warp - 2) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t srow = tmem_base + lane_off + (i ? kSCol1 : kSCol0);
+    const uint32_t orow = tmem_base + lane_off + (i ? kOCol1 : kOCol0);
+    const float k2 = p.scale_log2e;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(smem_u32(&s_full[i]), j & 1);
+      tc_fence_after();
+      const int kv_left = p.nkv - j * kKVTile;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c0 = 0; c0 < kKVTile; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(srow + c0, r);
+        tmem_ld_wait();
+        if (kv_left >= kKVTile) {
+#pragma unroll
+          for (int u = 0; u < 32; ++u) mx = fmaxf(mx, __uint_as_float(r[u]));
+        } else {
+#pragma unroll
+          for (int u = 0; u < 32; ++u) mx = fmaxf(mx, (c0 + u < kv_left) ? __uint_as_float(r[u]) : -INFINITY);
+        }
+      }
+      // lazy max update: only move the reference max when it grew by more than 8 in the exp2 domain
+      float alpha = 1.f;
+      const bool grow = (mx - m_run) * k2 > 8.f;   // also true on the first block (m_run = -inf)
+      if (grow) {
+        alpha = exp2f((m_run - mx) * k2);           // 0 on the first block
+        m_run = mx;
+      }
+      const float mk = m_run * k2;
+      float rs = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < kKVTile; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(srow + c0, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int u = 0; u < 32; u += 2) {
+          float e0 = exp2f(fmaf(__uint_as_float(r[u]), k2, -mk));
+          float e1 = exp2f(fmaf(__uint_as_float(r[u + 1]), k2, -mk));
+          if (kv_left < kKVTile) {
+            if (c0 + u >= kv_left) e0 = 0.f;
+            if (c0 + u + 1 >= kv_left) e1 = 0.f;
+          }
+          const __half2 h2 = __floats2half2_rn(e0, e1);
+          const float2 back = __half22float2(h2);
+          rs += back.x + back.y;
+          pk[u >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
+        tmem_st_x16(srow + (c0 >> 1), pk);  // P(fp16 pairs) over the already-consumed S columns
+      }
+      if (j > 0 && __any_sync(0xffffffffu, grow)) {
+        // PV_i(j-1) is complete (s_full(j) was committed after it): rescale this row of O
+#pragma unroll
+        for (int c0 = 0; c0 < DH; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_x32(orow + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 32; ++u) r[u] = __float_as_uint(__uint_as_float(r[u]) * alpha);
+          tmem_st_x32(orow + c0, r);
+        }
+      }
+      tmem_st_wait();
+      l_run = l_run * alpha + rs;
+      tc_fence_before();
+      mbar_arrive(smem_u32(&p_full[i]));
+    }
+    mbar_wait(smem_u32(&o_full), 0);
+    tc_fence_after();
+    const float inv = 1.f / l_run;
+    const int qi = q0 + i * 128 + row;
+    __half* optr = p.out + (static_cast<long long>(b) * p.nq + qi) * p.ldo + head * DH;
+#pragma unroll
+    for (int c0 = 0; c0 < DH; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_x32(orow + c0, r);
+      tmem_ld_wait();
+      if (qi < p.nq) {
+#pragma unroll
+        for (int u = 0; u < 32; u += 8) {
+          uint4 v;
+          v.x = pack_h2(__uint_as_float(r[u]) * inv, __uint_as_float(r[u + 1]) * inv);
+          v.y = pack_h2(__uint_as_float(r[u + 2]) * inv, __uint_as_float(r[u + 3]) * inv);
+          v.z = pack_h2(__uint_as_float(r[u + 4]) * inv, __uint_as_float(r[u + 5]) * inv);
+          v.w = pack_h2(__uint_as_float(r[u + 6]) * inv, __uint_as_float(r[u + 7]) * inv);
+          *reinterpret_cast<uint4*>(optr + c0 + u) = v;
+        }
+      }
+    }
+  }
+  (void)tile1_live;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int launch_attention_v2(const mgld_attention_desc* d, cudaStream_t stream) {
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.nq = d->nq; p.nkv = d->nkv; p.heads = d->heads; p.batch = d->batch;
+  p.q_col0 = d->q_col0; p.k_col0 = d->k_col0; p.v_col0 = d->v_col0;
+  p.q_hstride = d->q_head_stride; p.k_hstride = d->k_head_stride; p.v_hstride = d->v_head_stride;
+  p.kv_batched = d->kv_batched;
+  p.scale_log2e = d->scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<__half*>(d->out); p.ldo = d->ldo;
+  CUtensorMap tmQ, tmK, tmV;
+  {
+    uint64_t dims[3] = {(uint64_t)d->ldq, (uint64_t)d->nq, (uint64_t)d->batch};
+    uint64_t str[2] = {(uint64_t)d->ldq * 2, (uint64_t)d->ldq * 2 * d->nq};
+    uint32_t box[3] = {64, 128, 1};
+    int rc = make_tmap_f16(&tmQ, d->q, 3, dims, str, box);
+    if (rc) return rc;
+    const int kvb = d->kv_batched ? d->batch : 1;
+    uint64_t dimsk[3] = {(uint64_t)d->ldk, (uint64_t)d->nkv, (uint64_t)kvb};
+    uint64_t strk[2] = {(uint64_t)d->ldk * 2, (uint64_t)d->ldk * 2 * d->nkv};
+    rc = make_tmap_f16(&tmK, d->k, 3, dimsk, strk, box);
+    if (rc) return rc;
+    uint64_t dimsv[3] = {(uint64_t)d->ldv, (uint64_t)d->nkv, (uint64_t)kvb};
+    uint64_t strv[2] = {(uint64_t)d->ldv * 2, (uint64_t)d->ldv * 2 * d->nkv};
+    rc = make_tmap_f16(&tmV, d->v, 3, dimsv, strv, box);
+    if (rc) return rc;
+  }
+  const int smem = 2 * 16384 + kV2Stages * 2 * 16384 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MGLD_CUDA(cudaFuncSetAttribute(attention_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(d->nq, 256), d->heads, d->batch);
+  attention_v2_kernel<<<grid, kV2Threads, smem, stream>>>(tmQ, tmK, tmV, p);
+  MGLD_LAUNCH_CHECK("attention_v2_kernel");
+  return MGLD_OK;
+}
+
 }  // namespace mgld
 
 using namespace mgld;
@@ -298,6 +545,11 @@ extern "C" int mgld_attention(const mgld_attention_desc* d, void* stream) {
   MGLD_CHECK_ARG(d->ldq % 8 == 0 && d->ldk % 8 == 0 && d->ldv % 8 == 0 && d->ldo % 8 == 0,
                  "attention: row pitches must be multiples of 8 elements");
   MGLD_CHECK_ARG(d->q_col0 % 8 == 0 && d->k_col0 % 8 == 0 && d->v_col0 % 8 == 0, "attention: column offsets");
-  if (d->head_dim == 64) return launch_attention<64>(d, (cudaStream_t)stream);
+  if (d->head_dim == 64) {
+    // v2 (two query tiles per CTA, P in TMEM) pays off once there are >= 256 queries; MGLD_ATTN_V1=1 forces v1
+    static const bool force_v1 = getenv("MGLD_ATTN_V1") != nullptr;
+    if (!force_v1 && d->nq >= 256) return launch_attention_v2(d, (cudaStream_t)stream);
+    return launch_attention<64>(d, (cudaStream_t)stream);
+  }
   return launch_attention<128>(d, (cudaStream_t)stream);
 }

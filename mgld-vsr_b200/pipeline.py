@@ -214,3 +214,26 @@ def shard_segments(num_segments, world_size, rank):
     """segment s -> rank s % world_size (the reference's `seq_idx % n_gpus == select_idx`, script :338, applied to the
     independent 5-frame segments of one clip)."""
     return [s for s in range(num_segments) if s % world_size == rank]
+
+
+def gather_clip(local_segments, num_segments, frames_per_segment, world_size, rank, group=None):
+    """Stitch the output clip across ranks with ONE all-gather (NCCL on GPUs, gloo in the CPU tests).
+
+    local_segments: {segment_index: (frames_per_segment, 3, H, W) uint8} for the segments `shard_segments` gave this rank.
+    Ranks own ceil(num_segments / world_size) slots (unused slots are zero padding); returns the
+    (num_segments * frames_per_segment, 3, H, W) uint8 clip in segment order on every rank."""
+    import torch.distributed as dist
+    slots = (num_segments + world_size - 1) // world_size
+    sample = next(iter(local_segments.values()))
+    buf = torch.zeros(slots, *sample.shape, dtype=torch.uint8, device=sample.device)
+    for s, fr in local_segments.items():
+        assert s % world_size == rank
+        buf[s // world_size] = fr
+    out = torch.empty(world_size * slots, *sample.shape, dtype=torch.uint8, device=sample.device)
+    if world_size > 1:
+        dist.all_gather_into_tensor(out, buf, group=group)      # rank r's slots land at rows [r*slots, (r+1)*slots)
+    else:
+        out.copy_(buf)
+    out = out.view(world_size, slots, *sample.shape)
+    segs = [out[s % world_size, s // world_size] for s in range(num_segments)]
+    return torch.cat(segs, 0)
