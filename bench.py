@@ -117,34 +117,37 @@ class ClockSampler(threading.Thread):
 # reference arm / cpu baseline: the oracle on the host cores, bounded sample
 # ---------------------------------------------------------------------------------------------------------------------
 def cpu_reference_sample(cfg, steps=1, warmup=0, seed=0, verbose=False):
-    """Times ONE DDPM tile-step (struct encoder + UNet + posterior + guidance, T=5, 64x64 latent) of the oracle per step,
-    plus one VAE encoder pass and one temporal decoder pass at 512^2, on all host threads; extrapolates frames/s for the
-    full workload (2 segments x (50 tile-steps + 2 encoders + decoder))."""
+    """Bounded CPU sample (~10-30 s): the oracle's DDPM tile-step (struct encoder + UNet + stitch + posterior) on ONE frame
+    of the 5-frame segment (64x64 latent), one VAE-encoder pass and one temporal-decoder pass on one 512^2 frame.  All
+    three are linear in the number of frames (batch dimension; the temporal layers are <0.3 % of the FLOPs), so the
+    frames/s of the full workload is extrapolated as 2 segments x 5 frames x (50 tile-steps + 2 encoders + decoder)."""
     from oracle import torch_ref as R
     from mgld_vsr_b200.autoencoder import VideoAutoencoderKLResi
     from mgld_vsr_b200.unet import InflatedEncoderUNetModelWT, InflatedUNetModelDualcondV2
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    threads = min(cores, 32)          # torch's CPU conv/GEMM stop scaling (and regress) beyond ~32 threads at these sizes
+    torch.set_num_threads(threads)
     mp = cfg.model.params
     T = mp.num_frames
     ucfg, scfg, dd = dict(mp.unet_config.params), dict(mp.structcond_stage_config.params), dict(cfg.video_vae.params.ddconfig)
+    ucfg["num_frames"] = scfg["num_frames"] = dd["num_frames"] = 1
     sd_u = fast_state_dict(InflatedUNetModelDualcondV2(**ucfg).expected_shapes(), seed)
     sd_s = fast_state_dict(InflatedEncoderUNetModelWT(**scfg).expected_shapes(), seed + 1)
     sd_v = fast_state_dict(VideoAutoencoderKLResi(ddconfig=dd, embed_dim=4).expected_shapes(), seed + 2)
     _, resp, use = R.respaced_schedule(ddpm_steps=50)
     model = R.RefModel({**{"model.diffusion_model." + k: v for k, v in sd_u.items()},
-                        **{"structcond_stage_model." + k: v for k, v in sd_s.items()}}, ucfg, scfg, resp, use, T)
+                        **{"structcond_stage_model." + k: v for k, v in sd_s.items()}}, ucfg, scfg, resp, use, 1)
     g = torch.Generator().manual_seed(seed)
-    x, lat = torch.randn(T, 4, 64, 64, generator=g), torch.randn(T, 4, 64, 64, generator=g)
-    ctx, noise = torch.randn(1, 77, 1024, generator=g), torch.randn(T, 4, 64, 64, generator=g)
-    ff, fb = synthetic_flows(seed, 1, T, 64, 64)[0]
-    fo, bo = zip(*[R.forward_backward_consistency_check(fb[i:i + 1], ff[i:i + 1]) for i in range(T - 1)])
-    masks = (torch.stack(fo, 1)[:, :, None], torch.stack(bo, 1)[:, :, None])
+    x, lat = torch.randn(1, 4, 64, 64, generator=g), torch.randn(1, 4, 64, 64, generator=g)
+    ctx, noise = torch.randn(1, 77, 1024, generator=g), torch.randn(1, 4, 64, 64, generator=g)
     tw = R.gaussian_weights(64, 64, 1)
 
     def tile_step():
         with torch.no_grad():
-            return model.p_sample_canvas(x, ctx, lat, 25, noise, (ff[None], fb[None]), masks, -10.0, 64, 32, tw)[0]
+            return model.p_sample_canvas(x, ctx, lat, 25, noise, None, None, -10.0, 64, 32, tw)[0]
 
     times = []
     for i in range(warmup + steps):
@@ -154,21 +157,22 @@ def cpu_reference_sample(cfg, steps=1, warmup=0, seed=0, verbose=False):
         if i >= warmup:
             times.append(dt)
         if verbose:
-            print(f"[cpu] tile-step {dt:.2f}s", file=sys.stderr, flush=True)
-    t_step = sum(times) / len(times)
-    img = torch.rand(T, 3, 512, 512, generator=g) * 2 - 1
+            print(f"[cpu] 1-frame tile-step {dt:.2f}s", file=sys.stderr, flush=True)
+    t_step = T * sum(times) / len(times)
+    img = torch.rand(1, 3, 512, 512, generator=g) * 2 - 1
     with torch.no_grad():
         t0 = time.perf_counter()
         mom, fea = R.video_vae_encode(sd_v, dd, img)
-        t_enc = time.perf_counter() - t0
+        t_enc = T * (time.perf_counter() - t0)
         t0 = time.perf_counter()
-        R.video_vae_decode(sd_v, dd, torch.randn(T, 4, 64, 64, generator=g), fea, 1.0)
-        t_dec = time.perf_counter() - t0
+        R.video_vae_decode(sd_v, dd, torch.randn(1, 4, 64, 64, generator=g), fea, 1.0)
+        t_dec = T * (time.perf_counter() - t0)
     t_clip = 2 * (50 * t_step + 2 * t_enc + t_dec)
-    return {"value": N_FRAMES_CLIP / t_clip, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": (f"oracle/torch_ref.py fp32 on {cores} threads: {len(times)} DDPM tile-step(s) (struct-enc + UNet + "
-                       f"posterior + guidance, T=5, 64x64 latent) at {t_step:.2f} s each, one VAE encoder pass {t_enc:.2f} s, "
-                       f"one temporal decoder pass {t_dec:.2f} s at 512^2; extrapolated to 2 segments x (50 steps + 2 enc + dec)"),
+    return {"value": N_FRAMES_CLIP / t_clip, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": (f"oracle/torch_ref.py fp32 on {threads} threads ({cores} visible): {len(times)} one-frame DDPM tile-step(s) "
+                       f"(struct-enc + UNet + stitch + posterior, 64x64 latent), one one-frame VAE encoder pass and one one-frame "
+                       f"temporal decoder pass at 512^2; x5 frames -> tile-step {t_step:.2f} s, encoder {t_enc:.2f} s, decoder "
+                       f"{t_dec:.2f} s per 5-frame segment; extrapolated to 2 segments x (50 steps + 2 enc + dec)"),
             "tile_step_s": t_step, "vae_enc_s": t_enc, "vae_dec_s": t_dec}, t_step
 
 

@@ -77,6 +77,11 @@ typedef struct mgld_conv_gemm_desc {
   int32_t ldout;
   int32_t out_col0;
   int32_t out_f32;
+  /* optional fused GroupNorm statistics of the (fp16-rounded) output, for the GroupNorm that consumes it:
+     stats_out[t][g] += (sum, sum of squares) over frame t and channel group g of `stats_groups` equal groups;
+     fp64 [T, stats_groups, 2], zeroed by the caller.  Same layout mgld_gn_stats_f16 produces.                          */
+  double* stats_out;
+  int32_t stats_groups;
 } mgld_conv_gemm_desc;
 
 int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream);

@@ -16,7 +16,7 @@ import torch
 
 from . import ops as _cuda_ops
 from .ops import ACT_LRELU02, TAPS_1, TAPS_3X3, pack_conv_weight
-from .unet import _ModuleBase, _Packed, _TemporalConv, _Upsample, _gn_silu, as_nhwc_f16, nchw_view
+from .unet import StatsPool, _ModuleBase, _Packed, _TemporalConv, _Upsample, _gn_silu, _tag, as_nhwc_f16, nchw_view
 
 
 class DiagonalGaussianDistribution:
@@ -44,16 +44,18 @@ class _ResnetBlock:
         self.w2, self.b2 = P.conv(p + ".conv2")
         self.skip = P.conv(f"{p}.{skip_key}") if P.has(f"{p}.{skip_key}.weight") else None
 
-    def __call__(self, ops, x, x2=None, out=None):
+    def __call__(self, ops, x, x2=None, out=None, pool=None):
         a1 = _gn_silu(ops, x, self.n1, 1e-6, True, x2)
-        h = ops.conv_gemm(a1, self.w1, taps=TAPS_3X3, bias=self.b1)
+        s1 = pool.next() if pool is not None else None
+        h = _tag(ops.conv_gemm(a1, self.w1, taps=TAPS_3X3, bias=self.b1, stats_out=s1), s1)
         a2 = _gn_silu(ops, h, self.n2, 1e-6, True)
         if self.skip is not None:
             sk = ops.conv_gemm(x, self.skip[0], taps=TAPS_1, a2=x2, bias=self.skip[1])
         else:
             assert x2 is None
             sk = x
-        return ops.conv_gemm(a2, self.w2, taps=TAPS_3X3, bias=self.b2, res=sk, beta=1.0, out=out)
+        so = pool.next() if (pool is not None and out is None) else None
+        return _tag(ops.conv_gemm(a2, self.w2, taps=TAPS_3X3, bias=self.b2, res=sk, beta=1.0, out=out, stats_out=so), so)
 
 
 class _AttnBlock:
@@ -89,8 +91,9 @@ class _VaeDownsample:
     def __init__(self, P, p):
         self.w, self.b = P.conv(p + ".conv")
 
-    def __call__(self, ops, x):
-        return ops.conv_gemm(ops.im2col_s2(x, 0), self.w, taps=TAPS_1, bias=self.b)
+    def __call__(self, ops, x, pool=None):
+        so = pool.next() if pool is not None else None
+        return _tag(ops.conv_gemm(ops.im2col_s2(x, 0), self.w, taps=TAPS_1, bias=self.b, stats_out=so), so)
 
 
 class _Encoder:
@@ -110,17 +113,17 @@ class _Encoder:
         self.wout = pack_conv_weight(P.raw(p + "conv_out.weight").detach().float()).to(P.dev)
         self.bout = P.f32(p + "conv_out.bias")
 
-    def __call__(self, ops, x, return_fea=False):
+    def __call__(self, ops, x, return_fea=False, pool=None):
         h = ops.conv_small_cin(x.float().contiguous(), *self.conv_in)
         fea = []
         for lvl, (blocks, ds) in enumerate(self.down):
             for blk in blocks:
-                h = blk(ops, h)
+                h = blk(ops, h, pool=pool)
             if return_fea and lvl in (1, 2):
                 fea.append(h)
             if ds is not None:
-                h = ds(ops, h)
-        h = self.mid2(ops, self.attn(ops, self.mid1(ops, h)))
+                h = ds(ops, h, pool=pool)
+        h = self.mid2(ops, self.attn(ops, self.mid1(ops, h, pool=pool)), pool=pool)
         h = ops.conv3x3_small_cout(_gn_silu(ops, h, self.norm_out, 1e-6, True), self.wout, self.bout)
         return (h, fea) if return_fea else h
 
@@ -166,6 +169,7 @@ class AutoencoderKL(_ModuleBase):
                  colorize_nlabels=None, monitor=None, ops=None, **ignored):
         self.dd, self.embed_dim = dict(ddconfig), embed_dim
         self.ops = ops or _cuda_ops
+        self.pool = StatsPool()
         self.loaded = False
 
     def expected_shapes(self):
@@ -187,7 +191,8 @@ class AutoencoderKL(_ModuleBase):
 
     def encode(self, x, return_encfea=False):
         """autoencoder.py:347-353"""
-        moments = self.ops.conv_small_f32(self.encoder(self.ops, x), self.qw, self.qb)
+        self.pool.reset(x.shape[0], x.device)
+        moments = self.ops.conv_small_f32(self.encoder(self.ops, x, pool=self.pool), self.qw, self.qb)
         post = DiagonalGaussianDistribution(moments, self.ops)
         return (post, moments) if return_encfea else post
 
@@ -229,7 +234,7 @@ class _FuseBlock:
         self.rdbs = [_RDB(P, f"{p}.encode_enc_2.{i}", C) for i in range(num_block)]
         self.enc3 = _ResnetBlock(P, p + ".encode_enc_3", skip_key="conv_out")
 
-    def __call__(self, ops, enc_feat, dec_feat, w):
+    def __call__(self, ops, enc_feat, dec_feat, w, pool=None):
         T, H, W, C = dec_feat.shape
         bufs = [torch.zeros(T, H, W, C + 256, device=dec_feat.device, dtype=torch.float16) for _ in self.rdbs]
         self.enc1(ops, enc_feat, x2=dec_feat, out=bufs[0])          # writes columns [0, C)
@@ -238,7 +243,7 @@ class _FuseBlock:
             last = i == len(self.rdbs) - 1
             dst = torch.empty(T, H, W, C, device=dec_feat.device, dtype=torch.float16) if last else bufs[i + 1]
             e = rdb(ops, bufs[i], dst)
-        e = self.enc3(ops, e)
+        e = self.enc3(ops, e, pool=pool)
         return ops.axpby(dec_feat, e, 1.0, float(w))                 # dec + w * enc
 
 
@@ -265,20 +270,20 @@ class _VideoDecoder:
         self.wout = pack_conv_weight(P.raw(p + "conv_out.weight").detach().float()).to(P.dev)
         self.bout = P.f32(p + "conv_out.bias")
 
-    def __call__(self, ops, z, enc_fea):
+    def __call__(self, ops, z, enc_fea, pool=None):
         h = ops.conv_small_cin(z, *self.conv_in)
-        h = self.mid1(ops, h)
-        h = self.tmix(ops, h)
+        h = self.mid1(ops, h, pool=pool)
+        h = self.tmix(ops, h, pool=pool)
         h = self.attn(ops, h)
-        h = self.mid2(ops, h)
+        h = self.mid2(ops, h, pool=pool)
         for lvl in reversed(range(self.nres)):
             blocks, fuse, ups = self.up[lvl]
             for blk, tm in blocks:
-                h = tm(ops, blk(ops, h))
+                h = tm(ops, blk(ops, h, pool=pool), pool=pool)
             if fuse is not None:
-                h = fuse(ops, as_nhwc_f16(enc_fea[lvl - 1], ops), h, self.fusion_w)
+                h = fuse(ops, as_nhwc_f16(enc_fea[lvl - 1], ops), h, self.fusion_w, pool=pool)
             if ups is not None:
-                h = ups(ops, h)
+                h = ups(ops, h, pool=pool)
         return ops.conv3x3_small_cout(_gn_silu(ops, h, self.norm_out, 1e-6, True), self.wout, self.bout)
 
 
@@ -328,6 +333,7 @@ class VideoAutoencoderKLResi(_ModuleBase):
         self.dd, self.embed_dim = dict(ddconfig), embed_dim
         self.ops = ops or _cuda_ops
         self._fusion_w = fusion_w
+        self.pool = StatsPool()
         self.loaded = False
 
     def expected_shapes(self):
@@ -354,11 +360,13 @@ class VideoAutoencoderKLResi(_ModuleBase):
 
     def encode(self, x):
         """autoencoder.py:1674-1679 -> (posterior, enc_fea); enc_fea: NCHW-shaped fp16 (channels-last) feature taps."""
-        h, fea = self.encoder(self.ops, x, return_fea=True)
+        self.pool.reset(x.shape[0], x.device)
+        h, fea = self.encoder(self.ops, x, return_fea=True, pool=self.pool)
         moments = self.ops.conv_small_f32(h, self.qw, self.qb)
         return DiagonalGaussianDistribution(moments, self.ops), [nchw_view(f) for f in fea]
 
     def decode(self, z, enc_fea):
         """autoencoder.py:1687-1690 -> (T,3,H,W) fp32"""
+        self.pool.reset(z.shape[0], z.device)
         z = self.ops.conv_small_f32(z.float().contiguous(), self.pqw, self.pqb)
-        return self.decoder(self.ops, z, enc_fea)
+        return self.decoder(self.ops, z, enc_fea, pool=self.pool)

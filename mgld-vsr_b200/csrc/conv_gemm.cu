@@ -47,7 +47,9 @@ struct ConvGemmParams {
   const float* gn_weight;
   const float* gn_bias;
   int groups, ch_per_group;
-  uint32_t off_staging, off_hstage, off_bias;  // byte offsets from the 1024-aligned smem base
+  double* stats_out;      // optional fused GroupNorm statistics of the OUTPUT: [T, stat_groups, 2] (sum, sumsq), accumulated
+  int stat_groups, stat_cpg;
+  uint32_t off_staging, off_hstage, off_bias, off_stats;  // byte offsets from the 1024-aligned smem base
 };
 
 __device__ __forceinline__ void act_inplace32(float* v, int act) {
@@ -112,6 +114,47 @@ __device__ __forceinline__ void store_stage32_f32(uint8_t* staging, int row, int
     *reinterpret_cast<float4*>(base + ((ch ^ (row & 7)) << 4)) =
         make_float4(o[ch * 4], o[ch * 4 + 1], o[ch * 4 + 2], o[ch * 4 + 3]);
 }
+
+
+// Fused GroupNorm statistics of the output tile (consumer's grouping: stat_cpg channels per group).  Thread == row walks
+// its columns in increasing order, so it carries one (sum, sumsq) pair and flushes it at group boundaries: warp shuffle
+// reduction over the 32 rows of the warp (all in the same frame: BW*BH is a multiple of 32) -> shared table -> one
+// double atomicAdd per (frame, group) per tile.  Values are the fp16-rounded outputs, i.e. what the consumer will read.
+constexpr int kStatFrames = 4, kStatGroups = 72;
+struct StatAcc {
+  float s, q;
+  int g, next;
+  float* table;   // [kStatFrames][kStatGroups][2] in shared memory
+  int tf, g0, cpg, lane;
+  bool valid;
+  __device__ __forceinline__ void begin(int col, int cpg_, int g0_, int tf_, float* tab, bool valid_, int lane_) {
+    cpg = cpg_; g0 = g0_; tf = tf_; table = tab; valid = valid_; lane = lane_;
+    g = col / cpg; next = (g + 1) * cpg; s = 0.f; q = 0.f;
+  }
+  __device__ __forceinline__ void flush() {
+    float a = s, b = q;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if (lane == 0) {
+      float* t = table + (tf * kStatGroups + (g - g0)) * 2;
+      atomicAdd(t, a);
+      atomicAdd(t + 1, b);
+    }
+    s = 0.f; q = 0.f;
+  }
+  // v: 32 final fp32 values of columns [col, col+32); ncols = number of real output columns among them
+  __device__ __forceinline__ void add32(const float* v, int col, int ncols) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (i < ncols) {
+        if (col + i == next) { flush(); ++g; next += cpg; }
+        const float r = valid ? __half2float(__float2half_rn(v[i])) : 0.f;
+        s += r;
+        q = fmaf(r, r, q);
+      }
+    }
+  }
+};
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
@@ -235,6 +278,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* staging = smem_gen + p.off_staging;
     uint8_t* hstage = smem_gen + p.off_hstage;
     float* bias_s = reinterpret_cast<float*>(smem_gen + p.off_bias);
+    float* stat_s = reinterpret_cast<float*>(smem_gen + p.off_stats);
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       int x0, y0, t0, nt;
@@ -244,6 +288,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // bias tile -> smem (all threads passed the previous tile's closing barrier, so bias_s is free)
       for (int i = e; i < p.block_n; i += 128)
         bias_s[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+      StatAcc sa;
+      if (p.stats_out) {
+        for (int i = e; i < kStatFrames * kStatGroups * 2; i += 128) stat_s[i] = 0.f;
+        const int r_t = row / (p.BW * p.BH), r_y = (row / p.BW) % p.BH, r_x = row % p.BW;
+        const bool valid = (x0 + r_x < p.W) && (y0 + r_y < p.H) && (t0 + r_t < p.T);
+        sa.begin(nt * p.n_out_tile, p.stat_cpg, (nt * p.n_out_tile) / p.stat_cpg, (q * 32) / (p.BW * p.BH), stat_s, valid, lane);
+      }
       mbar_wait(smem_u32(&acc_full[buf]), (lt >> 1) & 1);
       tc_fence_after();
       if (p.has_res || pair_spade) mbar_wait(smem_u32(&res_full), lt & 1);
@@ -270,6 +321,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
           }
+          if (p.stats_out) sa.add32(v, nt * p.n_out_tile + c0, min(32, p.n_out_total - (nt * p.n_out_tile + c0)));
           if (p.out_f32) store_stage32_f32(staging, row, c0, v);
           else store_stage32(staging, row, c0, v, p.panel_cols);
         }
@@ -290,6 +342,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaf(p.alpha, v[i], p.beta * r[i]);
           }
+          if (p.stats_out) sa.add32(v, nt * 64 + c0, 32);
           store_stage32(staging, row, c0, v, 64);
         }
       } else {  // SPADE: out = beta*res + GNaffine(h) * (1 + gamma) + beta_s
@@ -315,15 +368,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 32; ++i) gm[i] = fmaf(p.beta, r[i], gm[i]);
           }
+          if (p.stats_out) sa.add32(gm, nt * 64 + c0, 32);
           store_stage32(staging, row, c0, gm, 64);
         }
       }
       // accumulator buffer drained -> the MMA warp may start tile lt+2 in it
       tc_fence_before();
       mbar_arrive(smem_u32(&acc_empty[buf]));
+      if (p.stats_out) sa.flush();
       // staging tile complete -> one thread issues the TMA stores
       fence_proxy_async_smem();
       named_bar_sync(1, 128);
+      if (p.stats_out) {
+        const int g0 = (nt * p.n_out_tile) / p.stat_cpg;
+        for (int i = e; i < kStatFrames * kStatGroups * 2; i += 128) {
+          const float val = stat_s[i];
+          const int tf = i / (kStatGroups * 2), gi = (i / 2) % kStatGroups;
+          if (val != 0.f && t0 + tf < p.T && g0 + gi < p.stat_groups)
+            atomicAdd(p.stats_out + (static_cast<long long>(t0 + tf) * p.stat_groups + g0 + gi) * 2 + (i & 1), (double)val);
+        }
+      }
       if (e == 0) {
         const int c0 = nt * p.n_out_tile;
         const int cols_per_panel = p.out_f32 ? 32 : p.panel_cols;
@@ -437,12 +501,20 @@ extern "C" int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream_) {
   p.has_res = d->res != nullptr; p.out_f32 = d->out_f32;
   p.gn_stats = d->gn_stats; p.gn_weight = d->gn_weight; p.gn_bias = d->gn_bias;
   p.groups = d->groups; p.ch_per_group = d->groups > 0 ? p.n_out_total / d->groups : 1;
+  p.stats_out = d->stats_out; p.stat_groups = d->stats_groups;
+  p.stat_cpg = d->stats_groups > 0 ? p.n_out_total / d->stats_groups : 1;
+  if (d->stats_out) {
+    MGLD_CHECK_ARG(d->stats_groups > 0 && p.n_out_total % d->stats_groups == 0 && !d->out_f32,
+                   "conv_gemm: stats_groups=%d must divide the %d output channels (fp16 out)", d->stats_groups, p.n_out_total);
+    MGLD_CHECK_ARG((p.BW * p.BH) % 32 == 0 && p.BT <= kStatFrames && p.n_out_tile / p.stat_cpg + 2 <= kStatGroups,
+                   "conv_gemm: fused statistics need >= 32 pixels per frame in a tile (box %dx%dx%d)", p.BW, p.BH, p.BT);
+  }
 
   // shared memory plan: [A/B ring][staging panels][h panel (SPADE)][bias]
   const int stage_bytes = kABytes + p.block_n * 128;
   const int staging_bytes = d->out_f32 ? p.n_panels * kPanelBytes : p.n_out_tile * kBlockM * 2;
   const int hstage_bytes = d->epilogue == MGLD_EPI_SPADE ? kPanelBytes : 0;
-  const int fixed = staging_bytes + hstage_bytes + 1024 /*bias*/ + 1024 /*alignment slack*/;
+  const int fixed = staging_bytes + hstage_bytes + 1024 /*bias*/ + kStatFrames * kStatGroups * 8 /*stats*/ + 1024 /*alignment slack*/;
   int stages = (224 * 1024 - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   MGLD_CHECK_ARG(stages >= 2, "conv_gemm: tile does not fit in shared memory (block_n=%d)", p.block_n);
@@ -450,7 +522,8 @@ extern "C" int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream_) {
   p.off_staging = stages * stage_bytes;
   p.off_hstage = p.off_staging + staging_bytes;
   p.off_bias = p.off_hstage + hstage_bytes;
-  const int smem = p.off_bias + 1024 + 1024;
+  p.off_stats = p.off_bias + 1024;
+  const int smem = p.off_stats + kStatFrames * kStatGroups * 2 * 4 + 1024;
 
   // tensor maps
   const int lda = d->lda > 0 ? d->lda : d->C1;

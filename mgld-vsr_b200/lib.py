@@ -36,6 +36,7 @@ class ConvGemmDesc(ctypes.Structure):
         ("groups", ctypes.c_int32),
         ("out", ctypes.c_void_p), ("ldout", ctypes.c_int32), ("out_col0", ctypes.c_int32),
         ("out_f32", ctypes.c_int32),
+        ("stats_out", ctypes.c_void_p), ("stats_groups", ctypes.c_int32),
     ]
 
 

@@ -49,7 +49,7 @@ def interleave_pair(wa, wb, blk=64):
 # ---------------------------------------------------------------------------------------------------------------
 def conv_gemm(a, w, *, taps=TAPS_1, a2=None, bias=None, epilogue=EPI_LINEAR, act=ACT_NONE, alpha=1.0, beta=0.0,
               res=None, h=None, gn_stats=None, gn_weight=None, gn_bias=None, groups=32, out=None, out_col0=0,
-              out_f32=False, block_n=0):
+              out_f32=False, block_n=0, stats_out=None, stats_groups=32):
     """Implicit-GEMM conv / linear on tcgen05 (mgld_conv_gemm).
 
     a: [T,H,W,C1] or [M,C1] fp16 (last dim contiguous);  w: packed [N, taps*(C1+C2)] fp16.
@@ -58,6 +58,8 @@ def conv_gemm(a, w, *, taps=TAPS_1, a2=None, bias=None, epilogue=EPI_LINEAR, act
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.is_cuda
     if a.dim() == 2:
         T, H, W = 1, 1, a.shape[0]
+    elif a.dim() == 3:          # [T, N, C] tokens: frames stay separate (needed for per-frame fused statistics)
+        T, H, W = a.shape[0], 1, a.shape[1]
     else:
         T, H, W = a.shape[0], a.shape[1], a.shape[2]
     C1 = a.shape[-1]
@@ -65,6 +67,8 @@ def conv_gemm(a, w, *, taps=TAPS_1, a2=None, bias=None, epilogue=EPI_LINEAR, act
     lda = a.stride(-2)
     if a.dim() == 4:
         assert a.stride(1) == lda * W and a.stride(0) == lda * W * H
+    elif a.dim() == 3:
+        assert a.stride(0) == lda * W
     C2, lda2 = 0, 0
     if a2 is not None:
         assert a2.shape[:-1] == a.shape[:-1] and a2.stride(-1) == 1
@@ -96,6 +100,9 @@ def conv_gemm(a, w, *, taps=TAPS_1, a2=None, bias=None, epilogue=EPI_LINEAR, act
     d.gn_bias = gn_bias.data_ptr() if gn_bias is not None else None
     d.groups = groups
     d.out, d.ldout, d.out_col0, d.out_f32 = out.data_ptr(), ldout, out_col0, int(out_f32)
+    if stats_out is not None:
+        assert stats_out.dtype == torch.float64 and stats_out.shape == (T, stats_groups, 2) and stats_out.is_contiguous()
+        d.stats_out, d.stats_groups = stats_out.data_ptr(), stats_groups
     _count(1)
     _L.check(_L.lib().mgld_conv_gemm(ctypes.byref(d), _L.stream_ptr()))
     return out

@@ -67,8 +67,36 @@ class _Packed:
         return self.f32(p + ".weight"), self.f32(p + ".bias")
 
 
+class StatsPool:
+    """fp64 (sum, sumsq) slots for GroupNorm statistics that producers accumulate in their GEMM epilogues.
+    One allocation + ONE memset per forward instead of a zero-fill launch per normalisation."""
+
+    def __init__(self, slots=256, groups=32):
+        self.slots, self.groups, self.buf, self.i = slots, groups, None, 0
+
+    def reset(self, T, device):
+        if self.buf is None or self.buf.shape[1] != T or self.buf.device != torch.device(device):
+            self.buf = torch.zeros(self.slots, T, self.groups, 2, device=device, dtype=torch.float64)
+        else:
+            self.buf.zero_()
+        self.i = 0
+
+    def next(self):
+        assert self.buf is not None and self.i < self.slots, "StatsPool exhausted / not reset"
+        self.i += 1
+        return self.buf[self.i - 1]
+
+
+def _tag(t, sums):
+    """remember the fused GroupNorm statistics of a producer's output on the tensor object"""
+    t._gn_sums = sums
+    return t
+
+
 def _gn_silu(ops, x, gb, eps, silu=True, x2=None):
-    sums = ops.gn_stats(x, x2)
+    sums = getattr(x, "_gn_sums", None) if x2 is None else None
+    if sums is None:
+        sums = ops.gn_stats(x, x2)
     return ops.gn_apply(x, sums, eps, gb[0], gb[1], silu, x2=x2)
 
 
@@ -92,23 +120,26 @@ class _ResBlock:
             wb, bb = P.conv(s + ".mlp_beta")
             self.wgb, self.bgb = interleave_pair(wg, wb), interleave_pair(bg, bb)
 
-    def __call__(self, ops, x, emb_bias, seg=None, x2=None):
+    def __call__(self, ops, x, emb_bias, seg=None, x2=None, pool=None):
         a1 = _gn_silu(ops, x, self.n1, 1e-5, True, x2)
-        h = ops.conv_gemm(a1, self.w1, taps=TAPS_3X3, bias=emb_bias[self.emb_idx])
+        s1 = pool.next() if pool is not None else None
+        h = _tag(ops.conv_gemm(a1, self.w1, taps=TAPS_3X3, bias=emb_bias[self.emb_idx], stats_out=s1), s1)
         a2 = _gn_silu(ops, h, self.n2, 1e-5, True)
         if self.skip is not None:
             sk = ops.conv_gemm(x, self.skip[0], taps=TAPS_1, a2=x2, bias=self.skip[1])
         else:
             assert x2 is None
             sk = x
+        so = pool.next() if pool is not None else None
         if not self.dual:
-            return ops.conv_gemm(a2, self.w2, taps=TAPS_3X3, bias=self.b2, res=sk, beta=1.0)
-        h2 = ops.conv_gemm(a2, self.w2, taps=TAPS_3X3, bias=self.b2)
+            return _tag(ops.conv_gemm(a2, self.w2, taps=TAPS_3X3, bias=self.b2, res=sk, beta=1.0, stats_out=so), so)
+        s2 = pool.next() if pool is not None else None
+        h2 = ops.conv_gemm(a2, self.w2, taps=TAPS_3X3, bias=self.b2, stats_out=s2)
         T, H, W, C = h2.shape
-        st = ops.gn_finalize(ops.gn_stats(h2), H * W, C, 1e-5)
+        st = ops.gn_finalize(s2 if s2 is not None else ops.gn_stats(h2), H * W, C, 1e-5)
         actv = ops.conv_gemm(seg, self.ws, taps=TAPS_3X3, bias=self.bs, act=ACT_RELU)
-        return ops.conv_gemm(actv, self.wgb, taps=TAPS_3X3, bias=self.bgb, epilogue=EPI_SPADE, h=h2, gn_stats=st,
-                             gn_weight=self.sn[0], gn_bias=self.sn[1], groups=32, res=sk, beta=1.0)
+        return _tag(ops.conv_gemm(actv, self.wgb, taps=TAPS_3X3, bias=self.bgb, epilogue=EPI_SPADE, h=h2, gn_stats=st,
+                                  gn_weight=self.sn[0], gn_bias=self.sn[1], groups=32, res=sk, beta=1.0, stats_out=so), so)
 
 
 class _EmbSlices:
@@ -179,7 +210,7 @@ class _SpatialTransformer:
         self.wff1, self.bff1 = interleave_pair(wf[:n], wf[n:]), interleave_pair(bf[:n], bf[n:])
         self.wff2, self.bff2 = P.conv(b + ".ff.net.2")
 
-    def __call__(self, ops, x, kv, kvc):
+    def __call__(self, ops, x, kv, kvc, pool=None):
         T, H, W, C = x.shape
         N, heads = H * W, self.heads
         dh = C // heads
@@ -200,8 +231,9 @@ class _SpatialTransformer:
         # GEGLU feed-forward
         g = ops.conv_gemm(ops.layernorm(t, *self.ln[2]), self.wff1, bias=self.bff1, epilogue=EPI_GEGLU)
         t = ops.conv_gemm(g, self.wff2, bias=self.bff2, res=t, beta=1.0)
-        out = ops.conv_gemm(t, self.wout, bias=self.bout, res=x.reshape(T * N, C), beta=1.0)
-        return out.reshape(T, H, W, C)
+        so = pool.next() if pool is not None else None
+        out = ops.conv_gemm(t.reshape(T, N, C), self.wout, bias=self.bout, res=x.reshape(T, N, C), beta=1.0, stats_out=so)
+        return _tag(out.reshape(T, H, W, C), so)
 
 
 class _TemporalConv:
@@ -212,8 +244,10 @@ class _TemporalConv:
         self.b = P.f32(p + ".temporal_conv.bias")
         self.alpha = float(P.raw(p + ".temporal_alpha").detach().float().reshape(-1)[0])
 
-    def __call__(self, ops, x):
-        return ops.conv_gemm(x, self.w, taps=TAPS_T3, bias=self.b, alpha=self.alpha, beta=1.0 - self.alpha, res=x)
+    def __call__(self, ops, x, pool=None):
+        so = pool.next() if pool is not None else None
+        return _tag(ops.conv_gemm(x, self.w, taps=TAPS_T3, bias=self.b, alpha=self.alpha, beta=1.0 - self.alpha, res=x,
+                                  stats_out=so), so)
 
 
 class _TemporalAttention:
@@ -227,30 +261,33 @@ class _TemporalAttention:
         self.wo, self.bo = P.conv(a + ".to_out.0")
         self.alpha = float(P.raw(p + ".temporal_alpha").detach().float().reshape(-1)[0])
 
-    def __call__(self, ops, x):
+    def __call__(self, ops, x, pool=None):
         T, H, W, C = x.shape
         n = ops.layernorm(x.reshape(T * H * W, C), *self.ln)
         qkv = ops.conv_gemm(n, self.wqkv).reshape(T, H * W, 3 * C)
         a = ops.temporal_attention(qkv, self.heads, (C // self.heads) ** -0.5)
-        out = ops.conv_gemm(a.reshape(T * H * W, C), self.wo, bias=self.bo, alpha=self.alpha, beta=1.0 - self.alpha,
-                            res=x.reshape(T * H * W, C))
-        return out.reshape(T, H, W, C)
+        so = pool.next() if pool is not None else None
+        out = ops.conv_gemm(a, self.wo, bias=self.bo, alpha=self.alpha, beta=1.0 - self.alpha,
+                            res=x.reshape(T, H * W, C), stats_out=so)
+        return _tag(out.reshape(T, H, W, C), so)
 
 
 class _Downsample:
     def __init__(self, P, p):
         self.w, self.b = P.conv(p + ".op")
 
-    def __call__(self, ops, x):
-        return ops.conv_gemm(ops.im2col_s2(x, 1), self.w, taps=TAPS_1, bias=self.b)
+    def __call__(self, ops, x, pool=None):
+        so = pool.next() if pool is not None else None
+        return _tag(ops.conv_gemm(ops.im2col_s2(x, 1), self.w, taps=TAPS_1, bias=self.b, stats_out=so), so)
 
 
 class _Upsample:
     def __init__(self, P, p):
         self.w, self.b = P.conv(p + ".conv")
 
-    def __call__(self, ops, x):
-        return ops.conv_gemm(ops.upsample2x(x), self.w, taps=TAPS_3X3, bias=self.b)
+    def __call__(self, ops, x, pool=None):
+        so = pool.next() if pool is not None else None
+        return _tag(ops.conv_gemm(ops.upsample2x(x), self.w, taps=TAPS_3X3, bias=self.b, stats_out=so), so)
 
 
 class _TimeEmbed:
@@ -311,6 +348,7 @@ class InflatedUNetModelDualcondV2(_ModuleBase):
                         semb_channels=semb_channels, num_frames=num_frames)
         self.num_frames = num_frames
         self.ops = ops or _cuda_ops
+        self.pool = StatsPool()
         self.loaded = False
 
     # ---- structure (mirrors openaimodel.py:2036-2257) -------------------------------------------------------------
@@ -466,18 +504,19 @@ class InflatedUNetModelDualcondV2(_ModuleBase):
             if kind == "conv_in":
                 h = ops.conv_small_cin(h, mod[0], mod[1])
             elif kind == "res":
-                h = mod(ops, h, emb_bias, seg[h.shape[2]], x2=h2)
+                h = mod(ops, h, emb_bias, seg[h.shape[2]], x2=h2, pool=self.pool)
                 h2 = None
             elif kind == "st":
-                h = mod(ops, h, kv, self.kvc)
+                h = mod(ops, h, kv, self.kvc, pool=self.pool)
             else:
-                h = mod(ops, h)
+                h = mod(ops, h, pool=self.pool)
         return h
 
     def forward(self, x, timesteps=None, context=None, struct_cond=None, y=None, **kwargs):
         assert self.loaded, "load_state_dict() first"
         assert y is None, "class-conditional models are not supported"
         ops = self.ops
+        self.pool.reset(x.shape[0], x.device)
         seg = {int(k): as_nhwc_f16(v, ops) for k, v in struct_cond.items()}
         emb = self.time_embed(ops, _t_scalar(timesteps, x.device))
         emb_bias = self.emb.run(ops, emb)
@@ -504,7 +543,7 @@ class _AttentionBlock:
         self.wqkv, self.bqkv = P.conv(p + ".qkv")
         self.wo, self.bo = P.conv(p + ".proj_out")
 
-    def __call__(self, ops, x):
+    def __call__(self, ops, x, pool=None):
         T, H, W, C = x.shape
         N, ch = H * W, C // self.heads
         xn = _gn_silu(ops, x, self.norm, 1e-5, silu=False)
@@ -512,8 +551,9 @@ class _AttentionBlock:
         a = ops.attention(qkv, qkv, qkv, batch=T, heads=self.heads, head_dim=ch, nq=N, nkv=N, scale=ch ** -0.5,
                           q_col0=0, k_col0=ch, v_col0=2 * ch, q_head_stride=3 * ch, k_head_stride=3 * ch,
                           v_head_stride=3 * ch)
-        out = ops.conv_gemm(a, self.wo, bias=self.bo, res=x.reshape(T * N, C), beta=1.0)
-        return out.reshape(T, H, W, C)
+        so = pool.next() if pool is not None else None
+        out = ops.conv_gemm(a.reshape(T, N, C), self.wo, bias=self.bo, res=x.reshape(T, N, C), beta=1.0, stats_out=so)
+        return _tag(out.reshape(T, H, W, C), so)
 
 
 class InflatedEncoderUNetModelWT(_ModuleBase):
@@ -530,6 +570,7 @@ class InflatedEncoderUNetModelWT(_ModuleBase):
                         num_res_blocks=num_res_blocks, attention_resolutions=list(attention_resolutions),
                         channel_mult=list(channel_mult), num_heads=num_heads, num_frames=num_frames)
         self.ops = ops or _cuda_ops
+        self.pool = StatsPool()
         self.loaded = False
 
     def layout(self):
@@ -626,15 +667,16 @@ class InflatedEncoderUNetModelWT(_ModuleBase):
             if kind == "conv_in":
                 h = ops.conv_small_cin(h, mod[0], mod[1])
             elif kind == "res":
-                h = mod(ops, h, emb_bias)
+                h = mod(ops, h, emb_bias, pool=self.pool)
             else:
-                h = mod(ops, h)
+                h = mod(ops, h, pool=self.pool)
         return h
 
     def forward(self, x, timesteps):
         """-> {'64': (T,256,64,64), '32': ..., ...}: NCHW-shaped fp16 tensors with channels-last storage."""
         assert self.loaded, "load_state_dict() first"
         ops = self.ops
+        self.pool.reset(x.shape[0], x.device)
         emb_bias = self.emb.run(ops, self.time_embed(ops, _t_scalar(timesteps, x.device)))
         results, h = [], x.float().contiguous()
         for mods in self.blocks:
@@ -645,6 +687,6 @@ class InflatedEncoderUNetModelWT(_ModuleBase):
         h = self._run(self.mid, h, emb_bias)
         results.append(h)
         assert len(results) == len(self.fea_tran)
-        return {str(r.shape[2]): nchw_view(self.fea_tran[i](ops, r, emb_bias)) for i, r in enumerate(results)}
+        return {str(r.shape[2]): nchw_view(self.fea_tran[i](ops, r, emb_bias, pool=self.pool)) for i, r in enumerate(results)}
 
     __call__ = forward

@@ -33,7 +33,7 @@ def _deinterleave(t, blk=64):
 
 def conv_gemm(a, w, *, taps=TAPS_1, a2=None, bias=None, epilogue=EPI_LINEAR, act=ACT_NONE, alpha=1.0, beta=0.0,
               res=None, h=None, gn_stats=None, gn_weight=None, gn_bias=None, groups=32, out=None, out_col0=0,
-              out_f32=False, block_n=0):
+              out_f32=False, block_n=0, stats_out=None, stats_groups=32):
     x = a if a2 is None else torch.cat([a, a2], dim=-1)
     shp = x.shape[:-1]
     C = x.shape[-1]
@@ -79,6 +79,9 @@ def conv_gemm(a, w, *, taps=TAPS_1, a2=None, bias=None, epilogue=EPI_LINEAR, act
             val = val + beta * res.float().reshape(M, -1)
     n_out = val.shape[1]
     dt = torch.float32 if out_f32 else torch.float16
+    if stats_out is not None:
+        vr = val.half().double().reshape(shp[0] if len(shp) >= 2 else 1, -1, stats_groups, n_out // stats_groups)
+        stats_out += torch.stack([vr.sum(dim=(1, 3)), (vr * vr).sum(dim=(1, 3))], dim=-1)
     if out is None:
         return val.to(dt).reshape(*shp, n_out)
     out[..., out_col0:out_col0 + n_out] = val.to(out.dtype).reshape(*out.shape[:-1], n_out)

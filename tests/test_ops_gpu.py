@@ -72,6 +72,23 @@ def test_conv_strided_views_and_column_offset():
     assert torch.equal(buf[..., C + 96:], ref_buf[..., C + 96:])     # untouched slots stay zero
 
 
+@pytest.mark.parametrize("T,H,W,Ci,Co,taps,res", [(5, 64, 64, 320, 320, 9, False), (5, 8, 8, 1280, 1280, 9, True),
+                                                  (5, 1, 1024, 640, 640, 1, True), (3, 30, 46, 128, 256, 9, False),
+                                                  (5, 16, 16, 256, 128, 9, False)])
+def test_fused_groupnorm_statistics(T, H, W, Ci, Co, taps, res):
+    """the (sum, sumsq) a conv epilogue accumulates for its consumer's GroupNorm == gn_stats of the stored output"""
+    O = ops()
+    x = rnd(T, H, W, Ci).half()
+    if H == 1:
+        x = x.reshape(T, W, Ci)
+    w = (rnd(Co, taps * Ci, scale=(taps * Ci) ** -0.5)).half()
+    r = rnd(*x.shape[:-1], Co).half() if res else None
+    sums = torch.zeros(T, 32, 2, device=DEV, dtype=torch.float64)
+    out = O.conv_gemm(x, w, taps=taps, bias=rnd(Co), res=r, beta=1.0 if res else 0.0, stats_out=sums)
+    ref = O.gn_stats(out.reshape(T, -1, Co))
+    assert rel_err(sums, ref) < 1e-5
+
+
 @pytest.mark.parametrize("T,H,W,C", [(5, 8, 8, 1280), (5, 32, 32, 256), (2, 12, 20, 128)])
 def test_temporal_conv(T, H, W, C):
     O = ops()
