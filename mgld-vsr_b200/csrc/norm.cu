@@ -56,7 +56,21 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, int C1, int ld1, 
     float s[8], q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
-    for (int r = rr; r < rows; r += rpi) {
+    int r = rr;
+    for (; r + 3 * rpi < rows; r += 4 * rpi) {   // 4 independent 16-byte loads in flight per thread
+      uint4 u[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        u[j] = load_cat8(x1, C1, ld1, x2, ld2, static_cast<long long>(t) * HW + r0 + r + j * rpi, v * 8);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float f[8];
+        unpack8(u[j], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+      }
+    }
+    for (; r < rows; r += rpi) {
       float f[8];
       unpack8(load_cat8(x1, C1, ld1, x2, ld2, static_cast<long long>(t) * HW + r0 + r, v * 8), f);
 #pragma unroll
@@ -117,11 +131,21 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, int ld1, 
     const long long m = static_cast<long long>(t) * HW + r;
     float f[8];
     unpack8(load_cat8(x1, C1, ld1, x2, ld2, m, v * 8), f);
+    // a vector of 8 channels touches at most two groups (cpg >= 4): [0, nb) in g, the rest in g + 1
+    const int g = (v * 8) / cpg, nb = (g + 1) * cpg - v * 8;
+    const float m0 = sh[2 * g], r0s = sh[2 * g + 1];
+    const float m1 = nb < 8 ? sh[2 * g + 2] : 0.f, r1s = nb < 8 ? sh[2 * g + 3] : 0.f;
+    float gm[8], bt[8];
+    if (gamma) {
+      const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), gb = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+      const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), bb = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+      gm[0] = ga.x; gm[1] = ga.y; gm[2] = ga.z; gm[3] = ga.w; gm[4] = gb.x; gm[5] = gb.y; gm[6] = gb.z; gm[7] = gb.w;
+      bt[0] = ba.x; bt[1] = ba.y; bt[2] = ba.z; bt[3] = ba.w; bt[4] = bb.x; bt[5] = bb.y; bt[6] = bb.z; bt[7] = bb.w;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int c = v * 8 + i, g = c / cpg;
-      float y = (f[i] - sh[2 * g]) * sh[2 * g + 1];
-      if (gamma) y = fmaf(y, __ldg(gamma + c), __ldg(beta + c));
+      float y = i < nb ? (f[i] - m0) * r0s : (f[i] - m1) * r1s;
+      if (gamma) y = fmaf(y, gm[i], bt[i]);
       if (silu) y = y / (1.f + __expf(-y));
       f[i] = y;
     }
@@ -164,8 +188,12 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, int ldx, int M, i
     const int v = lane + 32 * k;
     if (v < vpr) {
       float y[8];
+      const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), gb = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+      const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), bb = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+      const float gmv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+      const float btv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = fmaf((f[k][i] - mean) * rstd, __ldg(gamma + v * 8 + i), __ldg(beta + v * 8 + i));
+      for (int i = 0; i < 8; ++i) y[i] = fmaf((f[k][i] - mean) * rstd, gmv[i], btv[i]);
       *reinterpret_cast<uint4*>(out + static_cast<long long>(warp) * ldo + v * 8) = pack8(y);
     }
   }

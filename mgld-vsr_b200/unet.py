@@ -67,6 +67,13 @@ class _Packed:
         return self.f32(p + ".weight"), self.f32(p + ".bias")
 
 
+# Fusing the GroupNorm statistics of a conv's output into its epilogue (mgld_conv_gemm `stats_out`) removes one read
+# pass + one launch per normalisation, but measured on B200 (profiles/r01_dev_run7_*.log) the extra epilogue work costs
+# more than the standalone gn_stats kernels it replaces (UNet tile-step: conv_gemm +2.3 ms vs gn_stats -1.3 ms; VAE
+# decode +14 ms), because the epilogue is on the critical path of the short-K GEMMs.  Off by default; kept as an option.
+FUSE_GN_STATS = False
+
+
 class StatsPool:
     """fp64 (sum, sumsq) slots for GroupNorm statistics that producers accumulate in their GEMM epilogues.
     One allocation + ONE memset per forward instead of a zero-fill launch per normalisation."""
@@ -75,6 +82,8 @@ class StatsPool:
         self.slots, self.groups, self.buf, self.i = slots, groups, None, 0
 
     def reset(self, T, device):
+        if not FUSE_GN_STATS:
+            return
         if self.buf is None or self.buf.shape[1] != T or self.buf.device != torch.device(device):
             self.buf = torch.zeros(self.slots, T, self.groups, 2, device=device, dtype=torch.float64)
         else:
@@ -82,6 +91,8 @@ class StatsPool:
         self.i = 0
 
     def next(self):
+        if not FUSE_GN_STATS:
+            return None
         assert self.buf is not None and self.i < self.slots, "StatsPool exhausted / not reset"
         self.i += 1
         return self.buf[self.i - 1]
@@ -89,7 +100,8 @@ class StatsPool:
 
 def _tag(t, sums):
     """remember the fused GroupNorm statistics of a producer's output on the tensor object"""
-    t._gn_sums = sums
+    if sums is not None:
+        t._gn_sums = sums
     return t
 
 

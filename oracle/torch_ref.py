@@ -632,3 +632,137 @@ class RefModel:
             if return_eps:
                 eps_trace.append(e)
         return (img, eps_trace) if return_eps else img
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# RAFT_SR ("normal" model) — basicsr/archs/raft_arch.py
+# ---------------------------------------------------------------------------------------------------------------
+def _raft_norm(sd, p, x, kind):
+    if kind == "instance":
+        return F.instance_norm(x)                                       # nn.InstanceNorm2d defaults: eps 1e-5, no affine
+    if kind == "batch":
+        return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                            False, 0.0, 1e-5)
+    return x
+
+
+def _raft_resblock(sd, p, x, kind, stride):
+    """ResidualBlock.forward, raft_arch.py:127-136"""
+    y = F.relu(_raft_norm(sd, p + ".norm1", _conv(sd, p + ".conv1", x, stride=stride), kind))
+    y = F.relu(_raft_norm(sd, p + ".norm2", _conv(sd, p + ".conv2", y), kind))
+    if stride != 1:
+        x = _raft_norm(sd, p + ".norm3", _conv(sd, p + ".downsample.0", x, stride=stride, padding=0), kind)
+    return F.relu(x + y)
+
+
+def raft_encoder(sd, p, x, kind):
+    """BasicEncoder.forward, raft_arch.py:247-268"""
+    x = F.relu(_raft_norm(sd, p + ".norm1", _conv(sd, p + ".conv1", x, stride=2, padding=3), kind))
+    for li, stride in ((1, 1), (2, 2), (3, 2)):
+        x = _raft_resblock(sd, f"{p}.layer{li}.0", x, kind, stride)
+        x = _raft_resblock(sd, f"{p}.layer{li}.1", x, kind, 1)
+    return _conv(sd, p + ".conv2", x, padding=0)
+
+
+def _raft_bilinear_sampler(img, coords):
+    """raft_arch.py:517-532"""
+    H, W = img.shape[-2:]
+    xg, yg = coords.split([1, 1], dim=-1)
+    grid = torch.cat([2 * xg / (W - 1) - 1, 2 * yg / (H - 1) - 1], dim=-1)
+    return F.grid_sample(img, grid, align_corners=True)
+
+
+def raft_corr_pyramid(fmap1, fmap2, num_levels=4):
+    """CorrBlock.__init__ + CorrBlock.corr, raft_arch.py:37-55, 83-92"""
+    b, dim, ht, wd = fmap1.shape
+    corr = torch.matmul(fmap1.view(b, dim, ht * wd).transpose(1, 2), fmap2.view(b, dim, ht * wd))
+    corr = corr.view(b, ht, wd, 1, ht, wd) / torch.sqrt(torch.tensor(dim).float())
+    corr = corr.reshape(b * ht * wd, 1, ht, wd)
+    pyr = [corr]
+    for _ in range(num_levels - 1):
+        corr = F.avg_pool2d(corr, 2, stride=2)
+        pyr.append(corr)
+    return pyr
+
+
+def raft_corr_lookup(pyr, coords, radius=4):
+    """CorrBlock.__call__, raft_arch.py:57-81"""
+    r = radius
+    coords = coords.permute(0, 2, 3, 1)
+    b, h1, w1, _ = coords.shape
+    out = []
+    for i, corr in enumerate(pyr):
+        dx = torch.linspace(-r, r, 2 * r + 1)
+        dy = torch.linspace(-r, r, 2 * r + 1)
+        delta = torch.stack(torch.meshgrid(dy, dx, indexing="ij"), axis=-1).to(coords.device)
+        centroid = coords.reshape(b * h1 * w1, 1, 1, 2) / 2 ** i
+        c = _raft_bilinear_sampler(corr, centroid + delta.view(1, 2 * r + 1, 2 * r + 1, 2))
+        out.append(c.view(b, h1, w1, -1))
+    return torch.cat(out, dim=-1).permute(0, 3, 1, 2).contiguous().float()
+
+
+def _raft_update(sd, net, inp, corr, flow, p="update_block"):
+    """BasicUpdateBlock.forward raft_arch.py:476-486 with BasicMotionEncoder :436-445, SepConvGRU :398-412, FlowHead"""
+    e = p + ".encoder"
+    cor = F.relu(_conv(sd, e + ".convc1", corr, padding=0))
+    cor = F.relu(_conv(sd, e + ".convc2", cor))
+    flo = F.relu(_conv(sd, e + ".convf1", flow, padding=3))
+    flo = F.relu(_conv(sd, e + ".convf2", flo))
+    out = F.relu(_conv(sd, e + ".conv", torch.cat([cor, flo], dim=1)))
+    x = torch.cat([inp, out, flow], dim=1)
+    g = p + ".gru"
+    for sfx, pad in (("1", (0, 2)), ("2", (2, 0))):
+        hx = torch.cat([net, x], dim=1)
+        z = torch.sigmoid(_conv(sd, g + ".convz" + sfx, hx, padding=pad))
+        r = torch.sigmoid(_conv(sd, g + ".convr" + sfx, hx, padding=pad))
+        q = torch.tanh(_conv(sd, g + ".convq" + sfx, torch.cat([r * net, x], dim=1), padding=pad))
+        net = (1 - z) * net + z * q
+    delta = _conv(sd, p + ".flow_head.conv2", F.relu(_conv(sd, p + ".flow_head.conv1", net)))
+    mask = 0.25 * _conv(sd, p + ".mask.2", F.relu(_conv(sd, p + ".mask.0", net)), padding=0)
+    return net, mask, delta
+
+
+def raft_upsample_flow(flow, mask):
+    """RAFT_SR.upsample_flow, raft_arch.py:720-731 (convex combination, 8x)"""
+    N, _, H, W = flow.shape
+    mask = torch.softmax(mask.view(N, 1, 9, 8, 8, H, W), dim=2)
+    up = F.unfold(8 * flow, [3, 3], padding=1).view(N, 2, 9, 1, 1, H, W)
+    up = torch.sum(mask * up, dim=2).permute(0, 1, 4, 2, 5, 3)
+    return up.reshape(N, 2, 8 * H, 8 * W)
+
+
+def raft_forward(sd, ref, sup, iters=10, prefix=""):
+    """RAFT_SR.forward / process (model='normal'), raft_arch.py:733-808: flow from `ref` to `sup`, (N,2,H,W) pixels."""
+    sd = _strip(sd, prefix)
+    ht, wd = ref.shape[-2:]
+    pad_ht = (((ht // 8) + 1) * 8 - ht) % 8
+    pad_wd = (((wd // 8) + 1) * 8 - wd) % 8
+    pad = [pad_wd // 2, pad_wd - pad_wd // 2, pad_ht // 2, pad_ht - pad_ht // 2]      # InputPadder 'sintel', :17-27
+    im1, im2 = F.pad(ref, pad, mode="replicate"), F.pad(sup, pad, mode="replicate")
+    fm = raft_encoder(sd, "fnet", torch.cat([im1, im2], 0), "instance")
+    fmap1, fmap2 = torch.split(fm.float(), [im1.shape[0], im1.shape[0]], dim=0)
+    pyr = raft_corr_pyramid(fmap1, fmap2)
+    cnet = raft_encoder(sd, "cnet", im1, "batch")
+    net, inp = torch.split(cnet, [128, 128], dim=1)
+    net, inp = torch.tanh(net), torch.relu(inp)
+    N, _, H, W = im1.shape
+    ys, xs = torch.meshgrid(torch.arange(H // 8), torch.arange(W // 8), indexing="ij")
+    coords0 = torch.stack([xs, ys], dim=0).float()[None].repeat(N, 1, 1, 1).to(ref.device)
+    coords1 = coords0.clone()
+    flow_up = None
+    for _ in range(iters):
+        corr = raft_corr_lookup(pyr, coords1)
+        net, mask, delta = _raft_update(sd, net, inp, corr, coords1 - coords0)
+        coords1 = coords1 + delta
+        flow_up = raft_upsample_flow(coords1 - coords0, mask)
+    h2, w2 = flow_up.shape[-2:]
+    return flow_up[..., pad[2]:h2 - pad[3], pad[0]:w2 - pad[1]]
+
+
+def compute_flow(sd, lrs, prefix="flownet_model."):
+    """LatentDiffusionVSRTextWT.compute_flow, ddpm.py:3404-3429"""
+    n, t, c, h, w = lrs.shape
+    l1, l2 = lrs[:, :-1].reshape(-1, c, h, w), lrs[:, 1:].reshape(-1, c, h, w)
+    flows_backward = raft_forward(sd, l1, l2, prefix=prefix).view(n, t - 1, 2, h, w)
+    flows_forward = raft_forward(sd, l2, l1, prefix=prefix).view(n, t - 1, 2, h, w)
+    return flows_forward, flows_backward
