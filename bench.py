@@ -6,7 +6,7 @@ One "step" = one pass of the hot path over one clip per GPU: bicubic x4 -> VAE-e
 decode -> AdaIN colour fix, for the 2 five-frame segments of an 8-frame clip (the last segment is padded by repeating
 the last frame, script :345-346; only the 8 real frames are counted).  Weights are random-init at the reference's
 architecture (no checkpoints on the box), the text context is a random (1,77,1024) tensor, flows are synthetic smooth
-fields (RAFT is not on this path yet: see DESIGN.md), data = synthetic.
+fields only with --flow synthetic (default: RAFT_SR runs inside the timed path like in the reference), data = synthetic.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
@@ -47,6 +47,10 @@ def fast_state_dict(shapes, seed):
         s = tuple(s)
         if k.endswith("temporal_alpha"):
             sd[k] = torch.full(s, 0.5)
+        elif k.endswith("running_var"):
+            sd[k] = torch.ones(s)
+        elif k.endswith("running_mean") or k.endswith("num_batches_tracked"):
+            sd[k] = torch.zeros(s, dtype=torch.long if k.endswith("tracked") else torch.float32)
         elif len(s) == 1 and k.endswith(".weight"):
             sd[k] = torch.ones(s)
         elif k.endswith(".bias"):
@@ -192,7 +196,7 @@ def run_reference_arm(args, cfg):
 def workload_config(args, world):
     return {"workload": f"{N_FRAMES_CLIP}-frame 512x512 synthetic clip per GPU (2 segments of 5 frames, last frame padded), "
                         f"ddpm_steps={args.ddpm_steps}, SD-2.1 UNet shape (935M) + struct-cond encoder + temporal VAE, 1 UNet tile/step, "
-                        "motion guidance on (synthetic smooth flows; RAFT not in the timed path)",
+                        f"RAFT flow + occlusion masks + motion guidance on (flow={args.flow})",
             "frames_per_gpu": N_FRAMES_CLIP, "global_frames": N_FRAMES_CLIP * world, "ddpm_steps": args.ddpm_steps,
             "parallelism": f"clip-per-GPU x{world} + 1 NCCL all-gather" if world > 1 else "single GPU",
             "l2": "no flush needed: 2.3 GB of fp16 weights are re-streamed every DDPM step (>> 126 MB L2)"}
@@ -207,6 +211,8 @@ def main():
     ap.add_argument("--impl", default="mgld", choices=["mgld", "reference"])
     ap.add_argument("--ddpm-steps", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flow", default="raft", choices=["raft", "synthetic"],
+                    help="raft: RAFT_SR flow estimation inside the timed path (the reference's behaviour); synthetic: given flows")
     args = ap.parse_args()
     cfg = load_cfg()
     if args.impl == "reference":
@@ -236,8 +242,11 @@ def main():
     sd = {}
     for pre, mod, seed in (("model.diffusion_model.", model.model.diffusion_model, 0),
                            ("structcond_stage_model.", model.structcond_stage_model, 1),
-                           ("first_stage_model.", model.first_stage_model, 3)):
+                           ("first_stage_model.", model.first_stage_model, 3), ("flownet_model.", model.flownet_model, 4)):
         sd.update({pre + k: v for k, v in fast_state_dict(mod.expected_shapes(), seed).items()})
+    for k in sd:   # small random flow head: ten random-init GRU iterations stay bounded and the occlusion masks stay mixed
+        if k.startswith("flownet_model.update_block.flow_head.conv2"):
+            sd[k] = sd[k] * 0.02
     model.load_state_dict(sd, strict=False)
     del sd
     vq.load_state_dict(fast_state_dict(vq.expected_shapes(), 2), device=str(dev))
@@ -248,7 +257,7 @@ def main():
     T = cfg.model.params.num_frames
     n_seg = (N_FRAMES_CLIP + T - 1) // T
     clip_host = synthetic_clip(42 + rank).pin_memory()
-    flows = [(a.to(dev), b.to(dev)) for a, b in synthetic_flows(7 + rank, n_seg, T, 64, 64)]
+    flows = None if args.flow == "raft" else [(a.to(dev), b.to(dev)) for a, b in synthetic_flows(7 + rank, n_seg, T, 64, 64)]
     out_host = torch.empty(N_FRAMES_CLIP, 3, 512, 512).pin_memory()
     gather_buf = torch.empty(world * N_FRAMES_CLIP, 3, 512, 512, dtype=torch.uint8, device=dev) if world > 1 else None
 

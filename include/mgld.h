@@ -37,14 +37,16 @@ const char* mgld_last_error(void);
  * Replaces: F.conv2d 3x3/1x1 (openaimodel.py:401-445, spade.py:83-88, model.py:134-161), nn.Linear
  * (attention.py:48-75,510-524; openaimodel.py:2021-2025,418-424), Conv3d (3,1,1) (util.py:291-310).
  * ------------------------------------------------------------------------------------------------------------------ */
-enum mgld_taps { MGLD_TAPS_1 = 1, MGLD_TAPS_T3 = 3, MGLD_TAPS_3X3 = 9 };
+enum mgld_taps { MGLD_TAPS_1 = 1, MGLD_TAPS_T3 = 3 /* (3,1,1) in time */, MGLD_TAPS_3X3 = 9,
+                 MGLD_TAPS_1X5 = 5 /* RAFT SepConvGRU (1,5) */, MGLD_TAPS_5X1 = 6 /* (5,1): 5 taps along H */ };
 enum mgld_epilogue {
   MGLD_EPI_LINEAR = 0, /* v = act(acc + bias[n]);           out = alpha*v + beta*res[m,n]                        */
   MGLD_EPI_GEGLU = 1,  /* W rows interleaved per 128: 64 value | 64 gate;  out = (acc_v+b_v) * gelu(acc_g+b_g)    */
   MGLD_EPI_SPADE = 2   /* W rows interleaved per 128: 64 gamma | 64 beta;
                           out = beta_res*res + GNaffine(h)[m,c] * (1 + gamma) + beta   (spade.py:100-109)        */
 };
-enum mgld_act { MGLD_ACT_NONE = 0, MGLD_ACT_RELU = 1, MGLD_ACT_SILU = 2, MGLD_ACT_LRELU02 = 3, MGLD_ACT_GELU = 4 };
+enum mgld_act { MGLD_ACT_NONE = 0, MGLD_ACT_RELU = 1, MGLD_ACT_SILU = 2, MGLD_ACT_LRELU02 = 3, MGLD_ACT_GELU = 4,
+                MGLD_ACT_SIGMOID = 5, MGLD_ACT_TANH = 6 };
 
 typedef struct mgld_conv_gemm_desc {
   /* A operand: one or two NHWC fp16 tensors sharing (T,H,W); channels of a2 follow those of a (fused concat).      */
@@ -187,7 +189,32 @@ int mgld_temporal_attention_f16(const void* qkv, void* out, int t, int hw, int c
 /* DiagonalGaussianDistribution.sample * scale (distributions.py:24-37, ddpm.py:3382-3390)                              */
 int mgld_gaussian_sample_f32(const float* moments, const float* noise, float* out, int n, int cz, int h, int w,
                              float scale, void* stream);
-int mgld_axpby_f16(const void* x, const void* y, void* out, float a, float b, long long n, void* stream);
+/* out = [relu](a*x + b*y), fp16 */
+int mgld_axpby_f16(const void* x, const void* y, void* out, float a, float b, long long n, int relu, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * RAFT optical flow (basicsr/archs/raft_arch.py) — the non-GEMM pieces; its convolutions use mgld_conv_gemm
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* direct conv for Cin <= 4 (7x7 stems :215, :430): (N,Cin,H,W) fp32 -> NHWC fp16, stride 1|2, optional ReLU          */
+int mgld_conv_direct_f32(const float* in, const float* w, const float* bias, void* out, int n, int cin, int h, int wd,
+                         int cout, int ks, int stride, int pad, int ldo, int relu, void* stream);
+/* every second pixel of an NHWC fp16 tensor (input of the stride-2 1x1 `downsample` convs, :124-126)                  */
+int mgld_subsample2_f16(const void* in, void* out, int n, int h, int w, int c, void* stream);
+/* nn.InstanceNorm2d (no affine, eps) [+ReLU] from the per-(n,channel) sums of mgld_gn_stats_f16(groups = C)            */
+int mgld_instance_norm_apply_f16(const void* x, const double* sums, void* out, int n, int hw, int c, double eps,
+                                 int relu, void* stream);
+/* F.avg_pool2d(., 2, stride=2) on a stack of fp32 maps (correlation pyramid, :50-52)                                   */
+int mgld_avgpool2_f32(const float* in, float* out, long long n, int h, int w, void* stream);
+/* CorrBlock.__call__ (:57-81): 4 levels x 9x9 window bilinear lookup -> NHWC fp16 [b, h*w, ldo] (324 channels)          */
+int mgld_corr_lookup_f32(const float* l0, const float* l1, const float* l2, const float* l3, const float* coords,
+                         void* out, int b, int h, int w, int ldo, void* stream);
+/* SepConvGRU gating (:398-412): rnet = r * net;  net = (1 - z) * net + z * q;  zr = [M, 2C] = sigmoid(z | r)            */
+int mgld_gru_rh_f16(const void* zr, const void* net, void* rnet, long long m, int c, void* stream);
+int mgld_gru_update_f16(const void* zr, const void* q, void* net, long long m, int c, void* stream);
+/* copy a (B,Cs,h,w) fp32 tensor into columns [col0, col0+Cs) of an NHWC fp16 buffer (torch.cat([out, flow]), :445)     */
+int mgld_set_channels_f16(const float* src, void* dst, int b, int cs, int hw, int ld, int col0, void* stream);
+/* RAFT_SR.upsample_flow (:720-731): convex 8x upsampling, mask NHWC fp16 [b,h,w,576], flow (b,2,h,w) -> (b,2,8h,8w)     */
+int mgld_convex_upsample8_f32(const void* mask, const float* flow, float* out, int b, int h, int w, void* stream);
 
 #ifdef __cplusplus
 }

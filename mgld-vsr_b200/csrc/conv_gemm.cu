@@ -36,7 +36,7 @@ struct ConvGemmParams {
   int BW, BH, BT;
   int tiles_w, tiles_h, tiles_t, tiles_m, tiles_n;
   int kchunks1, kchunks;  // 64-wide chunks in source 1 / in both sources (per tap)
-  int taps;
+  int taps, tap_mode;  // taps = number of filter taps; tap_mode = enum mgld_taps (geometry)
   int N, block_n, n_out_tile, n_out_total, n_panels;
   int stages, tmem_cols, acc_stride;
   int panel_cols;  // fp16 output columns per staging panel: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B)
@@ -69,6 +69,14 @@ __device__ __forceinline__ void act_inplace32(float* v, int act) {
     case MGLD_ACT_GELU:
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
+      break;
+    case MGLD_ACT_SIGMOID:
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 1.f / (1.f + __expf(-v[i]));
+      break;
+    case MGLD_ACT_TANH:
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
       break;
     default: break;
   }
@@ -217,8 +225,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n0 = nt * p.block_n;
         for (int tap = 0; tap < p.taps; ++tap) {
           int dx = 0, dy = 0, dt = 0;
-          if (p.taps == 9) { dx = tap % 3 - 1; dy = tap / 3 - 1; }
-          else if (p.taps == 3) { dt = tap - 1; }
+          if (p.tap_mode == MGLD_TAPS_3X3) { dx = tap % 3 - 1; dy = tap / 3 - 1; }
+          else if (p.tap_mode == MGLD_TAPS_T3) { dt = tap - 1; }
+          else if (p.tap_mode == MGLD_TAPS_1X5) { dx = tap - 2; }
+          else if (p.tap_mode == MGLD_TAPS_5X1) { dy = tap - 2; }
           for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
             const int s = it % p.stages;
             const uint32_t ph = (it / p.stages) & 1;
@@ -456,7 +466,9 @@ extern "C" int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream_) {
                  "conv_gemm: C1=%d must be a multiple of 64 (or of 8 for a single-source 1-tap GEMM)", d->C1);
   MGLD_CHECK_ARG(d->C2 >= 0 && d->C2 % 64 == 0 && ((d->C2 > 0) == (d->a2 != nullptr)),
                  "conv_gemm: C2=%d must be a multiple of 64 and match a2", d->C2);
-  MGLD_CHECK_ARG(d->taps == 1 || d->taps == 3 || d->taps == 9, "conv_gemm: taps=%d", d->taps);
+  MGLD_CHECK_ARG(d->taps == MGLD_TAPS_1 || d->taps == MGLD_TAPS_T3 || d->taps == MGLD_TAPS_3X3 ||
+                     d->taps == MGLD_TAPS_1X5 || d->taps == MGLD_TAPS_5X1, "conv_gemm: taps=%d", d->taps);
+  const int ntaps = d->taps == MGLD_TAPS_5X1 ? 5 : d->taps;
   MGLD_CHECK_ARG(d->N > 0, "conv_gemm: N=%d", d->N);
   MGLD_CHECK_ARG(d->epilogue >= 0 && d->epilogue <= 2, "conv_gemm: epilogue=%d", d->epilogue);
   const bool pair = d->epilogue == MGLD_EPI_GEGLU || d->epilogue == MGLD_EPI_SPADE;
@@ -466,7 +478,8 @@ extern "C" int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream_) {
     MGLD_CHECK_ARG(d->h && d->gn_stats && d->gn_weight && d->gn_bias && d->groups > 0 &&
                        (d->N / 2) % d->groups == 0,
                    "conv_gemm: SPADE epilogue operands missing");
-  MGLD_CHECK_ARG(d->ldout % 8 == 0 && d->out_col0 % 8 == 0 && (!d->res || d->ldres % 8 == 0) &&
+  MGLD_CHECK_ARG((d->out_f32 ? d->ldout % 4 == 0 && d->out_col0 % 4 == 0 : d->ldout % 8 == 0 && d->out_col0 % 8 == 0) &&
+                     (!d->res || d->ldres % 8 == 0) &&
                      (!d->h || d->ldh % 8 == 0),
                  "conv_gemm: leading dimensions / column offset must be multiples of 8");
   MGLD_CHECK_ARG(!(d->out_f32 && d->res), "conv_gemm: residual with fp32 output is not supported");
@@ -481,7 +494,8 @@ extern "C" int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream_) {
   p.tiles_m = p.tiles_w * p.tiles_h * p.tiles_t;
   p.kchunks1 = ceil_div(d->C1, 64);
   p.kchunks = ceil_div(d->C1 + d->C2, 64);
-  p.taps = d->taps;
+  p.taps = ntaps;
+  p.tap_mode = d->taps;
   p.N = d->N;
   const int sms = num_sms();
   p.block_n = pair ? 128 : (d->block_n > 0 ? d->block_n : pick_block_n(d->N, p.tiles_m, sms));
@@ -490,7 +504,8 @@ extern "C" int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream_) {
   p.tiles_n = ceil_div(d->N, p.block_n);
   p.n_out_tile = pair ? 64 : p.block_n;
   p.n_out_total = pair ? d->N / 2 : d->N;
-  MGLD_CHECK_ARG(p.n_out_total % 8 == 0, "conv_gemm: output columns (%d) must be a multiple of 8", p.n_out_total);
+  // columns beyond n_out_total are clipped by the TMA store; only the row pitch needs 16-byte alignment
+  MGLD_CHECK_ARG(d->out_f32 ? d->ldout % 4 == 0 : d->ldout % 8 == 0, "conv_gemm: output row pitch %d not 16-byte aligned", d->ldout);
   p.panel_cols = (p.n_out_tile % 64 == 0) ? 64 : 32;
   p.n_panels = d->out_f32 ? p.n_out_tile / 32 : p.n_out_tile / p.panel_cols;
   p.acc_stride = p.block_n;  // multiple of 32 columns
@@ -540,7 +555,7 @@ extern "C" int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream_) {
     if (rc) return rc;
     if (d->a2) { rc = nhwc_map(&tmA2, d->a2, d->C2, lda2); if (rc) return rc; }
     else tmA2 = tmA;
-    const uint64_t K = (uint64_t)d->taps * (d->C1 + d->C2);
+    const uint64_t K = (uint64_t)ntaps * (d->C1 + d->C2);
     uint64_t dimsB[2] = {K, (uint64_t)d->N};
     uint64_t strB[1] = {K * 2};
     uint32_t boxB[2] = {64, (uint32_t)p.block_n};

@@ -311,7 +311,7 @@ __global__ void gaussian_sample_kernel(const float* __restrict__ moments, const 
 
 // out = a*x + b*y (fp16, vectorised) — residual adds that are not fused into a GEMM epilogue
 __global__ void axpby_f16_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, uint4* __restrict__ out,
-                                 float a, float b, long long nvec) {
+                                 float a, float b, long long nvec, int relu) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     const uint4 xv = __ldg(x + i), yv = __ldg(y + i);
     const __half2* xh = reinterpret_cast<const __half2*>(&xv);
@@ -321,7 +321,9 @@ __global__ void axpby_f16_kernel(const uint4* __restrict__ x, const uint4* __res
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float2 p = __half22float2(xh[k]), q = __half22float2(yh[k]);
-      oh[k] = __floats2half2_rn(a * p.x + b * q.x, a * p.y + b * q.y);
+      float r0 = a * p.x + b * q.x, r1 = a * p.y + b * q.y;
+      if (relu) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); }
+      oh[k] = __floats2half2_rn(r0, r1);
     }
     out[i] = o;
   }
@@ -434,9 +436,9 @@ extern "C" int mgld_gaussian_sample_f32(const float* moments, const float* noise
   MGLD_LAUNCH_CHECK("gaussian_sample_kernel");
   return MGLD_OK;
 }
-extern "C" int mgld_axpby_f16(const void* x, const void* y, void* out, float a, float b, long long n, void* stream) {
+extern "C" int mgld_axpby_f16(const void* x, const void* y, void* out, float a, float b, long long n, int relu, void* stream) {
   MGLD_CHECK_ARG(x && y && out && n > 0 && n % 8 == 0, "axpby: bad arguments");
-  axpby_f16_kernel<<<grid_1d(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)y, (uint4*)out, a, b, n / 8);
+  axpby_f16_kernel<<<grid_1d(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)y, (uint4*)out, a, b, n / 8, relu);
   MGLD_LAUNCH_CHECK("axpby_f16_kernel");
   return MGLD_OK;
 }

@@ -155,6 +155,8 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
         self.cond_stage_model = instantiate_from_config(cond_stage_config) if isinstance(cond_stage_config, dict) \
             else None
         self.structcond_stage_model = instantiate_from_config(structcond_stage_config, **extra)
+        if flownet_config and "params" in flownet_config and flownet_config["params"].get("load_path"):
+            flownet_config = {"target": flownet_config["target"], "params": {**flownet_config["params"], "load_path": None}}
         self.flownet_model = instantiate_from_config(flownet_config, **extra) if flownet_config else None
         self.register_schedule(given_betas=given_betas, beta_schedule=beta_schedule, timesteps=timesteps,
                                linear_start=linear_start, linear_end=linear_end, cosine_s=cosine_s)

@@ -17,9 +17,9 @@ def _count(n=1):
     LAUNCHES[0] += n
 
 
-TAPS_1, TAPS_T3, TAPS_3X3 = 1, 3, 9
+TAPS_1, TAPS_T3, TAPS_3X3, TAPS_1X5, TAPS_5X1 = 1, 3, 9, 5, 6
 EPI_LINEAR, EPI_GEGLU, EPI_SPADE = 0, 1, 2
-ACT_NONE, ACT_RELU, ACT_SILU, ACT_LRELU02, ACT_GELU = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_SILU, ACT_LRELU02, ACT_GELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4, 5, 6
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -74,7 +74,8 @@ def conv_gemm(a, w, *, taps=TAPS_1, a2=None, bias=None, epilogue=EPI_LINEAR, act
         assert a2.shape[:-1] == a.shape[:-1] and a2.stride(-1) == 1
         C2, lda2 = a2.shape[-1], a2.stride(-2)
     N = w.shape[0]
-    assert w.shape[1] == taps * (C1 + C2), (w.shape, taps, C1, C2)
+    ntaps = 5 if taps == TAPS_5X1 else taps
+    assert w.shape[1] == ntaps * (C1 + C2), (w.shape, taps, C1, C2)
     assert w.is_contiguous()
     n_out = N // 2 if epilogue in (EPI_GEGLU, EPI_SPADE) else N
     M = T * H * W
@@ -412,10 +413,101 @@ def gaussian_sample(moments, noise, scale):
     return out
 
 
-def axpby(x, y, a, b):
+def axpby(x, y, a, b, relu=False):
     assert x.dtype == torch.float16 and x.is_contiguous() and y.is_contiguous() and x.shape == y.shape
     out = torch.empty_like(x)
     _count(1)
     _L.check(_L.lib().mgld_axpby_f16(_L.ptr(x), _L.ptr(y), _L.ptr(out), ctypes.c_float(a), ctypes.c_float(b),
-                                     ctypes.c_longlong(x.numel()), _L.stream_ptr()))
+                                     ctypes.c_longlong(x.numel()), int(relu), _L.stream_ptr()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# RAFT pieces
+# ---------------------------------------------------------------------------------------------------------------
+def conv_direct(x, w, bias, stride=1, pad=0, relu=False):
+    """(N,Cin<=4,H,W) fp32, w fp32 [Cout,Cin,ks,ks] -> NHWC fp16 [N,Ho,Wo,Cout]"""
+    x = _f32c(x)
+    n, cin, h, wd = x.shape
+    cout, _, ks, _ = w.shape
+    ho, wo = (h + 2 * pad - ks) // stride + 1, (wd + 2 * pad - ks) // stride + 1
+    out = torch.empty(n, ho, wo, cout, device=x.device, dtype=torch.float16)
+    _count(1)
+    _L.check(_L.lib().mgld_conv_direct_f32(_L.ptr(x), _L.ptr(w), _L.ptr(bias), _L.ptr(out), n, cin, h, wd, cout, ks, stride,
+                                           pad, cout, int(relu), _L.stream_ptr()))
+    return out
+
+
+def subsample2(x):
+    assert x.dtype == torch.float16 and x.is_contiguous()
+    n, h, w, c = x.shape
+    out = torch.empty(n, (h + 1) // 2, (w + 1) // 2, c, device=x.device, dtype=torch.float16)
+    _count(1)
+    _L.check(_L.lib().mgld_subsample2_f16(_L.ptr(x), _L.ptr(out), n, h, w, c, _L.stream_ptr()))
+    return out
+
+
+def instance_norm(x, relu=False, eps=1e-5):
+    """nn.InstanceNorm2d (no affine) on NHWC fp16 [N,H,W,C]"""
+    assert x.dtype == torch.float16 and x.is_contiguous()
+    n, h, w, c = x.shape
+    sums = gn_stats(x.reshape(n, h * w, c), groups=c)
+    out = torch.empty_like(x)
+    _count(1)
+    _L.check(_L.lib().mgld_instance_norm_apply_f16(_L.ptr(x), _L.ptr(sums), _L.ptr(out), n, h * w, c, ctypes.c_double(eps),
+                                                   int(relu), _L.stream_ptr()))
+    return out
+
+
+def avgpool2_f32(x):
+    x = _f32c(x)
+    n, h, w = x.shape
+    out = torch.empty(n, h // 2, w // 2, device=x.device, dtype=torch.float32)
+    _count(1)
+    _L.check(_L.lib().mgld_avgpool2_f32(_L.ptr(x), _L.ptr(out), ctypes.c_longlong(n), h, w, _L.stream_ptr()))
+    return out
+
+
+def corr_lookup(levels, coords, out):
+    """levels: 4 fp32 tensors [B*h*w, h_l, w_l]; coords (B,2,h,w) fp32; out NHWC fp16 [B,h,w,ldo>=324] (written in place)"""
+    b, _, h, w = coords.shape
+    coords = _f32c(coords)
+    _count(1)
+    _L.check(_L.lib().mgld_corr_lookup_f32(_L.ptr(levels[0]), _L.ptr(levels[1]), _L.ptr(levels[2]), _L.ptr(levels[3]),
+                                           _L.ptr(coords), _L.ptr(out), b, h, w, out.shape[-1], _L.stream_ptr()))
+    return out
+
+
+def gru_rh(zr, net):
+    m, c = net.numel() // net.shape[-1], net.shape[-1]
+    out = torch.empty_like(net)
+    _count(1)
+    _L.check(_L.lib().mgld_gru_rh_f16(_L.ptr(zr), _L.ptr(net), _L.ptr(out), ctypes.c_longlong(m), c, _L.stream_ptr()))
+    return out
+
+
+def gru_update(zr, q, net):
+    """in place: net = (1 - z) * net + z * q"""
+    m, c = net.numel() // net.shape[-1], net.shape[-1]
+    _count(1)
+    _L.check(_L.lib().mgld_gru_update_f16(_L.ptr(zr), _L.ptr(q), _L.ptr(net), ctypes.c_longlong(m), c, _L.stream_ptr()))
+    return net
+
+
+def set_channels(src, dst, col0):
+    """src (B,Cs,h,w) fp32 -> dst NHWC fp16 [B,h,w,ld] columns [col0, col0+Cs)"""
+    src = _f32c(src)
+    b, cs, h, w = src.shape
+    _count(1)
+    _L.check(_L.lib().mgld_set_channels_f16(_L.ptr(src), _L.ptr(dst), b, cs, h * w, dst.shape[-1], col0, _L.stream_ptr()))
+    return dst
+
+
+def convex_upsample8(mask, flow):
+    """mask NHWC fp16 [B,h,w,576], flow (B,2,h,w) fp32 -> (B,2,8h,8w) fp32"""
+    flow = _f32c(flow)
+    b, _, h, w = flow.shape
+    out = torch.empty(b, 2, 8 * h, 8 * w, device=flow.device, dtype=torch.float32)
+    _count(1)
+    _L.check(_L.lib().mgld_convex_upsample8_f32(_L.ptr(mask), _L.ptr(flow), _L.ptr(out), b, h, w, _L.stream_ptr()))
     return out

@@ -59,3 +59,26 @@ def det_state_dict(shapes):
 def rel_err(a, b):
     a, b = a.float(), b.float()
     return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()
+
+
+def raft_state_dict(shapes):
+    """deterministic RAFT weights: positive BatchNorm running_var, the duplicated norm3 / downsample.1 entries of the
+    reference's state_dict kept identical (they are one module there), and a small flow head so that ten random-init
+    GRU iterations stay bounded."""
+    sd = {}
+    for k, shp in shapes.items():
+        shp = tuple(shp)
+        if k.endswith("running_var"):
+            sd[k] = 0.5 + det_tensor(k, shp).abs()
+        elif k.endswith("num_batches_tracked"):
+            sd[k] = torch.zeros((), dtype=torch.long)
+        elif k.endswith("running_mean"):
+            sd[k] = 0.1 * det_tensor(k, shp)
+        else:
+            sd[k] = det_state_dict({k: shp})[k]
+    for k in list(sd):
+        if ".downsample.1." in k:
+            sd[k.replace(".downsample.1.", ".norm3.")] = sd[k]
+        if k.startswith("update_block.flow_head.conv2"):
+            sd[k] = sd[k] * 0.02
+    return sd

@@ -10,9 +10,9 @@ import torch
 import torch.nn.functional as F
 
 LAUNCHES = [0]
-TAPS_1, TAPS_T3, TAPS_3X3 = 1, 3, 9
+TAPS_1, TAPS_T3, TAPS_3X3, TAPS_1X5, TAPS_5X1 = 1, 3, 9, 5, 6
 EPI_LINEAR, EPI_GEGLU, EPI_SPADE = 0, 1, 2
-ACT_NONE, ACT_RELU, ACT_SILU, ACT_LRELU02, ACT_GELU = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_SILU, ACT_LRELU02, ACT_GELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4, 5, 6
 
 from mgld_vsr_b200.ops import pack_conv_weight, pack_temporal_weight, interleave_pair  # pure-torch layout helpers
 
@@ -22,6 +22,8 @@ def _act(v, act):
     if act == ACT_SILU: return F.silu(v)
     if act == ACT_LRELU02: return F.leaky_relu(v, 0.2)
     if act == ACT_GELU: return F.gelu(v)
+    if act == ACT_SIGMOID: return torch.sigmoid(v)
+    if act == ACT_TANH: return torch.tanh(v)
     return v
 
 
@@ -42,6 +44,11 @@ def conv_gemm(a, w, *, taps=TAPS_1, a2=None, bias=None, epilogue=EPI_LINEAR, act
     N = w.shape[0]
     if taps == 1:
         acc = xf.reshape(-1, C) @ wf.t()
+    elif taps in (TAPS_1X5, TAPS_5X1):
+        T, H, W = shp
+        kh, kw = (1, 5) if taps == TAPS_1X5 else (5, 1)
+        wt = wf.reshape(N, kh, kw, C).permute(0, 3, 1, 2)
+        acc = F.conv2d(xf.permute(0, 3, 1, 2), wt, padding=(kh // 2, kw // 2)).permute(0, 2, 3, 1).reshape(-1, N)
     elif taps == 9:
         T, H, W = shp
         wt = wf.reshape(N, 3, 3, C).permute(0, 3, 1, 2)
@@ -220,8 +227,57 @@ def gaussian_sample(moments, noise, scale):
     return (mean + std * noise if noise is not None else mean) * scale
 
 
-def axpby(x, y, a, b):
-    return (a * x.float() + b * y.float()).half()
+def axpby(x, y, a, b, relu=False):
+    r = a * x.float() + b * y.float()
+    return (F.relu(r) if relu else r).half()
+
+
+def conv_direct(x, w, bias, stride=1, pad=0, relu=False):
+    y = F.conv2d(x.float(), w.float(), bias, stride=stride, padding=pad)
+    return (F.relu(y) if relu else y).permute(0, 2, 3, 1).contiguous().half()
+
+
+def subsample2(x):
+    return x[:, ::2, ::2].contiguous()
+
+
+def instance_norm(x, relu=False, eps=1e-5):
+    y = F.instance_norm(x.float().permute(0, 3, 1, 2), eps=eps)
+    return (F.relu(y) if relu else y).permute(0, 2, 3, 1).contiguous().half()
+
+
+def avgpool2_f32(x):
+    return F.avg_pool2d(x[:, None], 2, stride=2)[:, 0]
+
+
+def corr_lookup(levels, coords, out):
+    from oracle.torch_ref import raft_corr_lookup
+    b, _, h, w = coords.shape
+    c = raft_corr_lookup([l[:, None] for l in levels], coords)          # (B, 324, h, w)
+    out[..., :324] = c.permute(0, 2, 3, 1).half()
+    return out
+
+
+def gru_rh(zr, net):
+    c = net.shape[-1]
+    return (zr.float().reshape(-1, 2 * c)[:, c:].reshape(net.shape) * net.float()).half()
+
+
+def gru_update(zr, q, net):
+    c = net.shape[-1]
+    z = zr.float().reshape(-1, 2 * c)[:, :c].reshape(net.shape)
+    net.copy_(((1 - z) * net.float() + z * q.float()).half())
+    return net
+
+
+def set_channels(src, dst, col0):
+    dst[..., col0:col0 + src.shape[1]] = src.permute(0, 2, 3, 1).half()
+    return dst
+
+
+def convex_upsample8(mask, flow):
+    from oracle.torch_ref import raft_upsample_flow
+    return raft_upsample_flow(flow, mask.float().permute(0, 3, 1, 2))
 
 
 # ---- flow ops: emulated with the same torch ops the reference uses -------------------------------------------------

@@ -8,7 +8,7 @@ import torch
 import torch.nn.functional as F
 
 import emu_ops
-from common import GOLDEN, TINY_DD, TINY_STRUCT, TINY_UNET, det_state_dict, det_tensor, rel_err
+from common import GOLDEN, TINY_DD, TINY_STRUCT, TINY_UNET, det_state_dict, det_tensor, raft_state_dict, rel_err
 from oracle import torch_ref as R
 
 T = 2
@@ -140,3 +140,16 @@ def test_flow_api_argument_errors():
         flow.forward_backward_consistency_check(torch.zeros(1, 3, 8, 8), torch.zeros(1, 2, 8, 8), ops=emu_ops)
     out = flow.flow_warp(torch.ones(1, 2, 8, 8), torch.zeros(1, 8, 8, 2), ops=emu_ops)
     assert torch.allclose(out, torch.ones(1, 2, 8, 8))
+
+
+def test_raft_host_graph():
+    """channel padding (96->128, 324->384), BatchNorm folding, fused z|r GEMM, two-source GRU inputs, last-iteration-only
+    convex upsampling: all invisible in the result"""
+    from mgld_vsr_b200.raft import RAFT_SR
+    gold = torch.load(os.path.join(GOLDEN, "raft.pt"))
+    m = RAFT_SR(ops=emu_ops)
+    m.load_state_dict(raft_state_dict(m.expected_shapes()), device="cpu")
+    a, b = det_tensor("raft_a", (2, 3, 128, 136)).sigmoid(), det_tensor("raft_b", (2, 3, 128, 136)).sigmoid()
+    assert rel_err(m(a, b, iters=10), gold["flow"]) < 5e-3
+    with pytest.raises(AssertionError):
+        m(a, b[:, :, :64])

@@ -10,7 +10,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from common import GOLDEN, TINY_DD, TINY_STRUCT, TINY_UNET, det_state_dict, det_tensor, rel_err
+from common import GOLDEN, TINY_DD, TINY_STRUCT, TINY_UNET, det_state_dict, det_tensor, raft_state_dict, rel_err
 from oracle import torch_ref as R
 
 pytestmark = pytest.mark.gpu
@@ -136,3 +136,18 @@ def test_sample_untiled_runs_and_matches_canvas_single_tile():
     b = m.sample_canvas(cond=ctx, struct_cond=lat, batch_size=T, timesteps=S, time_replace=S, x_T=x_T, tile_size=32,
                         tile_overlap=16, batch_size_sample=1)
     assert rel_err(a, b) < 2e-3
+
+
+def test_raft_vs_oracle_and_golden():
+    from mgld_vsr_b200.raft import RAFT_SR
+    m = RAFT_SR()
+    sd = raft_state_dict(m.expected_shapes())
+    m.load_state_dict(sd)
+    a, b = det_tensor("raft_a", (2, 3, 128, 136)).sigmoid().to(DEV), det_tensor("raft_b", (2, 3, 128, 136)).sigmoid().to(DEV)
+    got = m(a, b, iters=10)
+    ref = R.raft_forward(to_dev(sd), a, b, iters=10)
+    assert rel_err(got, ref) < 1e-2
+    assert rel_err(got.cpu(), torch.load(os.path.join(GOLDEN, "raft.pt"))["flow"]) < 1e-2
+    # odd sizes exercise the replicate padding and the non-16-byte-aligned correlation rows
+    a, b = torch.rand(1, 3, 130, 150, device=DEV), torch.rand(1, 3, 130, 150, device=DEV)
+    assert rel_err(m(a, b, iters=3), R.raft_forward(to_dev(sd), a, b, iters=3)) < 1e-2

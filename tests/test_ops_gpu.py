@@ -253,3 +253,46 @@ def test_canvas_posterior():
     got, ge = O.canvas_posterior_f32(x, tiles, tw, noise, *args, want_eps=True)
     ref, re_ = E.canvas_posterior_f32(x, tiles, tw, noise, *args, want_eps=True)
     assert rel_err(ge, re_) < 1e-6 and rel_err(got, ref) < 1e-6
+
+
+def test_raft_ops():
+    O = ops()
+    # 1x5 / 5x1 taps + sigmoid / tanh epilogues, two sources (the SepConvGRU shape)
+    net, x = rnd(4, 16, 17, 128).half(), rnd(4, 16, 17, 256).half()
+    for taps, kk in ((O.TAPS_1X5, (1, 5)), (O.TAPS_5X1, (5, 1))):
+        w = O.pack_conv_weight(rnd(256, 384, *kk, scale=(5 * 384) ** -0.5))
+        b = rnd(256)
+        for act in (O.ACT_SIGMOID, O.ACT_TANH):
+            kw = dict(taps=taps, a2=x, bias=b, act=act)
+            assert rel_err(O.conv_gemm(net, w, **kw), E.conv_gemm(net, w, **kw)) < 4e-3
+    # stems, subsample, instance norm
+    img = rnd(3, 3, 40, 56)
+    w7, b7 = rnd(64, 3, 7, 7, scale=0.08), rnd(64)
+    assert rel_err(O.conv_direct(img, w7, b7, stride=2, pad=3, relu=True), E.conv_direct(img, w7, b7, stride=2, pad=3, relu=True)) < 2e-3
+    xh = rnd(3, 20, 28, 128).half()
+    assert torch.equal(O.subsample2(xh), E.subsample2(xh))
+    for relu in (False, True):
+        assert rel_err(O.instance_norm(xh, relu=relu), E.instance_norm(xh, relu=relu)) < 3e-3
+    assert rel_err(O.axpby(xh, xh.flip(0), 1.0, 1.0, relu=True), E.axpby(xh, xh.flip(0), 1.0, 1.0, relu=True)) < 2e-3
+    # correlation pyramid + lookup
+    B, h, w = 2, 16, 17
+    corr = rnd(B * h * w, h, w)
+    levels = [corr]
+    for _ in range(3):
+        levels.append(O.avgpool2_f32(levels[-1]))
+        assert rel_err(levels[-1], E.avgpool2_f32(levels[-2])) < 1e-6
+    ys, xs = torch.meshgrid(torch.arange(h, device=DEV), torch.arange(w, device=DEV), indexing="ij")
+    coords = torch.stack([xs, ys], 0).float()[None].repeat(B, 1, 1, 1) + rnd(B, 2, h, w) * 2
+    got = O.corr_lookup(levels, coords, torch.zeros(B, h, w, 384, device=DEV, dtype=torch.float16))
+    ref = E.corr_lookup([l.cpu() for l in levels], coords.cpu(), torch.zeros(B, h, w, 384, dtype=torch.float16))
+    assert rel_err(got.cpu(), ref) < 2e-3 and got[..., 324:].abs().max() == 0
+    # GRU gating, channel insert, convex upsampling
+    zr, q, nt = rnd(B, h, w, 256).sigmoid().half(), rnd(B, h, w, 128).tanh().half(), rnd(B, h, w, 128).half()
+    assert rel_err(O.gru_rh(zr, nt), E.gru_rh(zr, nt)) < 2e-3
+    n1, n2 = nt.clone(), nt.clone()
+    assert rel_err(O.gru_update(zr, q, n1), E.gru_update(zr, q, n2)) < 2e-3
+    fl = rnd(B, 2, h, w)
+    buf1, buf2 = torch.zeros(B, h, w, 256, device=DEV, dtype=torch.float16), torch.zeros(B, h, w, 256, device=DEV, dtype=torch.float16)
+    assert torch.equal(O.set_channels(fl, buf1, 254), E.set_channels(fl, buf2, 254))
+    mask = rnd(B, h, w, 576).half()
+    assert rel_err(O.convex_upsample8(mask, fl), E.convex_upsample8(mask, fl)) < 1e-4

@@ -12,7 +12,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from common import GOLDEN, TINY_DD, TINY_STRUCT, TINY_UNET, det_state_dict, det_tensor, rel_err
+from common import GOLDEN, TINY_DD, TINY_STRUCT, TINY_UNET, det_state_dict, det_tensor, raft_state_dict, rel_err
 from oracle import torch_ref as R
 
 T = 2
@@ -75,6 +75,16 @@ def test_flow_and_guidance_oracle_vs_golden():
     out = R.guidance_update(z, (ff, fb), (g["fwd_occ"], g["bwd_occ"]), Tn, -10.0, -2.3)
     assert rel_err(out, g["out"]) < 1e-6
     assert 0.05 < g["fwd_occ"].mean() < 0.95
+
+
+def test_raft_oracle_vs_golden():
+    from mgld_vsr_b200.raft import RAFT_SR
+    gold = torch.load(os.path.join(GOLDEN, "raft.pt"))
+    sd = raft_state_dict(RAFT_SR().expected_shapes())
+    a, b = det_tensor("raft_a", (2, 3, 128, 136)).sigmoid(), det_tensor("raft_b", (2, 3, 128, 136)).sigmoid()
+    with torch.no_grad():
+        assert rel_err(R.raft_forward(sd, a, b, iters=10), gold["flow"]) < 1e-5
+    assert gold["flow"].abs().max() > 0.05
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -164,6 +174,20 @@ def test_modules_vs_reference_live():
         {k: tuple(v) for k, v in _shapes("VideoAutoencoderKLResi", ddconfig=TINY_DD).items()}
     assert {k: tuple(v.shape) for k, v in se.state_dict().items()} == \
         {k: tuple(v) for k, v in _shapes("InflatedEncoderUNetModelWT", **TINY_STRUCT).items()}
+
+
+@pytest.mark.reference
+def test_raft_manifest_and_forward_vs_reference_live():
+    ra = _ref("basicsr.archs.raft_arch")
+    with contextlib.redirect_stdout(io.StringIO()):
+        raft = ra.RAFT_SR(model="normal", load_path=None).eval()
+    from mgld_vsr_b200.raft import RAFT_SR
+    assert {k: tuple(v.shape) for k, v in raft.state_dict().items()} == {k: tuple(v) for k, v in RAFT_SR().expected_shapes().items()}
+    sd = raft_state_dict({k: v.shape for k, v in raft.state_dict().items()})
+    raft.load_state_dict(sd)
+    a, b = torch.rand(1, 3, 130, 150), torch.rand(1, 3, 130, 150)        # sizes that need the replicate padding
+    with torch.no_grad():
+        assert rel_err(R.raft_forward(sd, a, b, iters=4), raft(a, b, iters=4)) < 1e-5
 
 
 @pytest.mark.reference

@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 import torch.nn.functional as F
 
-from common import GOLDEN, TINY_DD, TINY_STRUCT, TINY_UNET, det_state_dict, det_tensor
+from common import GOLDEN, TINY_DD, TINY_STRUCT, TINY_UNET, det_state_dict, det_tensor, raft_state_dict
 from oracle import ref_shim
 
 T = 2
@@ -65,6 +65,15 @@ def main():
                     "warp_nearest": au.flow_warp(xf, fl.permute(0, 2, 3, 1), interp_mode="nearest"),
                     "resize": au.resize_flow(fl, "shape", (23, 31)), "fwd_occ": fo, "bwd_occ": bo},
                    os.path.join(GOLDEN, "flow_ops.pt"))
+    # --- RAFT ------------------------------------------------------------------------------------------------------------
+    ra = ref_shim.ref("basicsr.archs.raft_arch")
+    raft = quiet(ra.RAFT_SR, model="normal", load_path=None).eval()
+    rsd = raft_state_dict({k: v.shape for k, v in raft.state_dict().items()})
+    raft.load_state_dict(rsd)
+    a = det_tensor("raft_a", (2, 3, 128, 136)).sigmoid()
+    b = det_tensor("raft_b", (2, 3, 128, 136)).sigmoid()
+    with torch.no_grad():
+        torch.save({"flow": raft(a, b, iters=10)}, os.path.join(GOLDEN, "raft.pt"))
     # --- guidance (reference's own compute_temporal_condition_v4 + autograd) ----------------------------------------
     dd = ref_shim.ref("ldm.models.diffusion.ddpm")
     Tn = 4
