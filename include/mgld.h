@@ -84,9 +84,16 @@ typedef struct mgld_conv_gemm_desc {
      fp64 [T, stats_groups, 2], zeroed by the caller.  Same layout mgld_gn_stats_f16 produces.                          */
   double* stats_out;
   int32_t stats_groups;
+  /* optional scratch for the split-K path (layers with too few output tiles to fill the SMs: partial fp32 tiles are
+     written per K-slice and reduced in a fixed order by a second kernel).  Size: mgld_conv_gemm_workspace_bytes().
+     NULL / too small = single-pass execution.                                                                        */
+  void* workspace;
+  int64_t workspace_bytes;
 } mgld_conv_gemm_desc;
 
 int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream);
+/* bytes of workspace with which mgld_conv_gemm would use split-K for this problem (0 = it would not)                   */
+long long mgld_conv_gemm_workspace_bytes(const mgld_conv_gemm_desc* d);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Fused softmax attention on tcgen05:  out = softmax(scale * Q K^T) V     (fp16 in/out, fp32 accumulate)

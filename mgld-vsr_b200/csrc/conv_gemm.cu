@@ -37,6 +37,7 @@ struct ConvGemmParams {
   int tiles_w, tiles_h, tiles_t, tiles_m, tiles_n;
   int kchunks1, kchunks;  // 64-wide chunks in source 1 / in both sources (per tap)
   int taps, tap_mode;  // taps = number of filter taps; tap_mode = enum mgld_taps (geometry)
+  int split_k, k_per_split, slab_frames;  // split-K: work unit = (tile, split); partial fp32 tiles go to slab `split`
   int N, block_n, n_out_tile, n_out_total, n_panels;
   int stages, tmem_cols, acc_stride;
   int panel_cols;  // fp16 output columns per staging panel: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B)
@@ -181,7 +182,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int stage_bytes = kABytes + p.block_n * kKChunk * 2;
   const int num_k = p.taps * p.kchunks;
-  const int total_tiles = p.tiles_m * p.tiles_n;
+  const int total_tiles = p.tiles_m * p.tiles_n * p.split_k;  // work units
   const bool pair_spade = p.epilogue == MGLD_EPI_SPADE;
 
   if (threadIdx.x == 0) {
@@ -207,7 +208,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = tmem_base_slot;
 
   // tile -> coordinates; consecutive tiles share the weight tile (n) and walk the pixel boxes (L2-friendly)
-  auto tile_coords = [&](int tile, int& x0, int& y0, int& t0, int& nt) {
+  auto tile_coords = [&](int unit, int& x0, int& y0, int& t0, int& nt) {
+    const int tile = unit / p.split_k;   // the splits of one tile run on neighbouring CTAs
     const int tm = tile % p.tiles_m;
     nt = tile / p.tiles_m;
     x0 = (tm % p.tiles_w) * p.BW;
@@ -223,23 +225,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int x0, y0, t0, nt;
         tile_coords(tile, x0, y0, t0, nt);
         const int n0 = nt * p.block_n;
-        for (int tap = 0; tap < p.taps; ++tap) {
+        const int kb = (tile % p.split_k) * p.k_per_split, ke = min(kb + p.k_per_split, num_k);
+        for (int k = kb; k < ke; ++k, ++it) {
+          const int tap = k / p.kchunks, kc = k - tap * p.kchunks;
           int dx = 0, dy = 0, dt = 0;
           if (p.tap_mode == MGLD_TAPS_3X3) { dx = tap % 3 - 1; dy = tap / 3 - 1; }
           else if (p.tap_mode == MGLD_TAPS_T3) { dt = tap - 1; }
           else if (p.tap_mode == MGLD_TAPS_1X5) { dx = tap - 2; }
           else if (p.tap_mode == MGLD_TAPS_5X1) { dy = tap - 2; }
-          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-            const int s = it % p.stages;
-            const uint32_t ph = (it / p.stages) & 1;
-            mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
-            const uint32_t fb = smem_u32(&full_bar[s]);
-            const uint32_t sa = smem_base + s * stage_bytes;
-            mbar_expect_tx(fb, stage_bytes);
-            if (kc < p.kchunks1) tma_load_4d(sa, &tmA, fb, kc * kKChunk, x0 + dx, y0 + dy, t0 + dt);
-            else tma_load_4d(sa, &tmA2, fb, (kc - p.kchunks1) * kKChunk, x0 + dx, y0 + dy, t0 + dt);
-            tma_load_2d(sa + kABytes, &tmB, fb, (tap * p.kchunks + kc) * kKChunk, n0);
-          }
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          const uint32_t sa = smem_base + s * stage_bytes;
+          mbar_expect_tx(fb, stage_bytes);
+          if (kc < p.kchunks1) tma_load_4d(sa, &tmA, fb, kc * kKChunk, x0 + dx, y0 + dy, t0 + dt);
+          else tma_load_4d(sa, &tmA2, fb, (kc - p.kchunks1) * kKChunk, x0 + dx, y0 + dy, t0 + dt);
+          tma_load_2d(sa + kABytes, &tmB, fb, k * kKChunk, n0);
         }
         if (p.has_res || pair_spade) {
           // residual (and SPADE's h) tile of THIS output tile, into the staging buffers the epilogue will overwrite
@@ -265,7 +267,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(smem_u32(&acc_empty[buf]), ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t dcol = tmem_base + buf * p.acc_stride;
-        for (int k = 0; k < num_k; ++k, ++it) {
+        const int kb = (tile % p.split_k) * p.k_per_split, ke = min(kb + p.k_per_split, num_k);
+        for (int k = kb; k < ke; ++k, ++it) {
           const int s = it % p.stages;
           mbar_wait(smem_u32(&full_bar[s]), (it / p.stages) & 1);
           tc_fence_after();
@@ -274,7 +277,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t bdesc = umma_smem_desc(sa + kABytes, 0, 1024, kSwz128);
 #pragma unroll
           for (int kk = 0; kk < kKChunk / 16; ++kk)
-            umma_ss(dcol, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0);  // +32 B along K per step
+            umma_ss(dcol, adesc + 2 * kk, bdesc + 2 * kk, idesc, ((k - kb) | kk) != 0);  // +32 B along K per step
           umma_commit(smem_u32(&empty_bar[s]));
         }
         umma_commit(smem_u32(&acc_full[buf]));
@@ -404,7 +407,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int pbytes = (!p.out_f32 && p.panel_cols == 32) ? kPanelBytes / 2 : kPanelBytes;
         for (int pn = 0; pn < p.n_panels; ++pn) {
           if (c0 + pn * cols_per_panel < p.n_out_total)
-            tma_store_4d(&tmOut, smem_base + p.off_staging + pn * pbytes, c0 + pn * cols_per_panel, x0, y0, t0);
+            tma_store_4d(&tmOut, smem_base + p.off_staging + pn * pbytes, c0 + pn * cols_per_panel, x0, y0,
+                         t0 + (tile % p.split_k) * p.slab_frames);
         }
         tma_store_commit();
         tma_store_wait_read();  // staging may be overwritten (by the next residual load / next tile's epilogue)
@@ -421,6 +425,111 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
+}
+
+
+// Split-K finalize: sum the S partial fp32 tiles of every output element in a fixed order (deterministic) and apply the
+// epilogue the single-pass kernel would have applied.  ws: [S][slab_frames][H][W][ldws] fp32 raw accumulators.
+struct SplitFinalizeParams {
+  const float* ws;
+  long long slab_stride;  // floats between slabs
+  int S, T, H, W, ldws;
+  int N, n_out_total, epilogue, act;
+  const float* bias;
+  float alpha, beta;
+  const __half* res; int ldres;
+  const __half* h; int ldh;
+  const float* gn_stats; const float* gn_weight; const float* gn_bias; int groups, ch_per_group;
+  __half* out; int ldout, out_col0;
+};
+__device__ __forceinline__ float act1(float v, int act) {
+  switch (act) {
+    case MGLD_ACT_RELU: return fmaxf(v, 0.f);
+    case MGLD_ACT_SILU: return v / (1.f + __expf(-v));
+    case MGLD_ACT_LRELU02: return v > 0.f ? v : 0.2f * v;
+    case MGLD_ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+    case MGLD_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
+    case MGLD_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+__global__ void splitk_finalize_kernel(const SplitFinalizeParams p) {
+  const int vpr = (p.n_out_total + 7) >> 3;
+  const long long M = static_cast<long long>(p.T) * p.H * p.W;
+  const long long total = M * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / vpr;
+    const int c = (int)(i - m * vpr) * 8;
+    const bool pair = p.epilogue != MGLD_EPI_LINEAR;
+    const int ca = pair ? (c >> 6) * 128 + (c & 63) : c;   // raw accumulator column of the first half of a pair
+    float a[8], b[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { a[u] = 0.f; b[u] = 0.f; }
+    for (int s = 0; s < p.S; ++s) {
+      const float* row = p.ws + s * p.slab_stride + m * p.ldws;
+      const float4 x0 = *reinterpret_cast<const float4*>(row + ca), x1 = *reinterpret_cast<const float4*>(row + ca + 4);
+      a[0] += x0.x; a[1] += x0.y; a[2] += x0.z; a[3] += x0.w; a[4] += x1.x; a[5] += x1.y; a[6] += x1.z; a[7] += x1.w;
+      if (pair) {
+        const float4 y0 = *reinterpret_cast<const float4*>(row + ca + 64), y1 = *reinterpret_cast<const float4*>(row + ca + 68);
+        b[0] += y0.x; b[1] += y0.y; b[2] += y0.z; b[3] += y0.w; b[4] += y1.x; b[5] += y1.y; b[6] += y1.z; b[7] += y1.w;
+      }
+    }
+    float r[8];
+    if (p.res) {
+      const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + m * p.ldres + c));
+      const __half2* hh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const float2 f = __half22float2(hh[u]); r[2 * u] = f.x; r[2 * u + 1] = f.y; }
+    }
+    float o[8];
+    if (p.epilogue == MGLD_EPI_LINEAR) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float v = a[u] + ((p.bias && c + u < p.N) ? __ldg(p.bias + c + u) : 0.f);
+        v = p.alpha * act1(v, p.act);
+        o[u] = p.res ? fmaf(p.beta, r[u], v) : v;
+      }
+    } else if (p.epilogue == MGLD_EPI_GEGLU) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float v = a[u] + (p.bias ? __ldg(p.bias + ca + u) : 0.f), g = b[u] + (p.bias ? __ldg(p.bias + ca + 64 + u) : 0.f);
+        const float y = v * act1(g, MGLD_ACT_GELU);
+        o[u] = p.res ? fmaf(p.alpha, y, p.beta * r[u]) : y;
+      }
+    } else {
+      const int t = (int)(m / (static_cast<long long>(p.H) * p.W));
+      const uint4 hr = __ldg(reinterpret_cast<const uint4*>(p.h + m * p.ldh + c));
+      const __half2* hh = reinterpret_cast<const __half2*>(&hr);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int cc = c + u, g = cc / p.ch_per_group;
+        const float2 st = __ldg(reinterpret_cast<const float2*>(p.gn_stats) + t * p.groups + g);
+        const float2 f = __half22float2(hh[u >> 1]);
+        const float hv = (u & 1) ? f.y : f.x;
+        const float xn = fmaf((hv - st.x) * st.y, __ldg(p.gn_weight + cc), __ldg(p.gn_bias + cc));
+        const float gm = a[u] + (p.bias ? __ldg(p.bias + ca + u) : 0.f), bt = b[u] + (p.bias ? __ldg(p.bias + ca + 64 + u) : 0.f);
+        const float y = fmaf(xn, 1.f + gm, bt);
+        o[u] = p.res ? fmaf(p.beta, r[u], y) : y;
+      }
+    }
+    uint4 pk;
+    pk.x = pack_h2(o[0], o[1]); pk.y = pack_h2(o[2], o[3]); pk.z = pack_h2(o[4], o[5]); pk.w = pack_h2(o[6], o[7]);
+    *reinterpret_cast<uint4*>(p.out + m * p.ldout + p.out_col0 + c) = pk;
+  }
+}
+
+// split-K plan: only when a single pass would leave most SMs idle and K is long enough to amortise the second pass
+static int pick_split_k(int tiles, int num_k, int sms) {
+  if (tiles * 10 >= sms * 6 || num_k < 16) return 1;
+  int best = 1;
+  double best_util = (double)tiles / sms;
+  for (int S = 2; S <= 8; ++S) {
+    if (num_k / S < 8) break;
+    const int units = tiles * S;
+    const double util = (double)units / ((double)((units + sms - 1) / sms) * sms);
+    if (util > best_util * 1.08) { best_util = util; best = S; }
+  }
+  return best;
 }
 
 static int pick_block_n(int N, int tiles_m, int sms) {
@@ -456,7 +565,7 @@ static bool g_attr_set = false;
 
 using namespace mgld;
 
-extern "C" int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream_) {
+static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int split_k, int slab_frames) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!initialised()) { set_error("mgld_init() has not been called"); return MGLD_ERR_NOT_INIT; }
   MGLD_CHECK_ARG(d && d->a && d->w && d->out, "conv_gemm: null pointer");
@@ -502,6 +611,7 @@ extern "C" int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream_) {
   if (d->out_f32 && p.block_n > 128) p.block_n = 128;  // fp32 staging tile: 128 x 128 x 4 B = 64 KB
   MGLD_CHECK_ARG(p.block_n % 32 == 0 && p.block_n >= 32 && p.block_n <= 256, "conv_gemm: block_n=%d", p.block_n);
   p.tiles_n = ceil_div(d->N, p.block_n);
+  p.split_k = split_k; p.k_per_split = ceil_div(ntaps * p.kchunks, split_k); p.slab_frames = slab_frames;
   p.n_out_tile = pair ? 64 : p.block_n;
   p.n_out_total = pair ? d->N / 2 : d->N;
   // columns beyond n_out_total are clipped by the TMA store; only the row pitch needs 16-byte alignment
@@ -562,7 +672,8 @@ extern "C" int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream_) {
     rc = make_tmap_f16(&tmB, d->w, 2, dimsB, strB, boxB);
     if (rc) return rc;
     if (d->out_f32) {
-      uint64_t dims[4] = {(uint64_t)p.n_out_total, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->T};
+      uint64_t dims[4] = {(uint64_t)p.n_out_total, (uint64_t)d->W, (uint64_t)d->H,
+                          (uint64_t)(split_k > 1 ? split_k * slab_frames : d->T)};
       uint64_t str[3] = {(uint64_t)d->ldout * 4, (uint64_t)d->ldout * 4 * d->W, (uint64_t)d->ldout * 4 * d->W * d->H};
       uint32_t box32[4] = {32, (uint32_t)p.BW, (uint32_t)p.BH, (uint32_t)p.BT};
       rc = make_tmap_f32(&tmOut, reinterpret_cast<const float*>(d->out) + d->out_col0, 4, dims, str, box32);
@@ -580,9 +691,70 @@ extern "C" int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream_) {
     MGLD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     g_attr_set = true;
   }
-  const int total_tiles = p.tiles_m * p.tiles_n;
+  const int total_tiles = p.tiles_m * p.tiles_n * p.split_k;
   dim3 grid(total_tiles < sms ? total_tiles : sms, 1, 1);
   conv_gemm_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmA2, tmB, tmOut, tmRes, tmH, p);
   MGLD_LAUNCH_CHECK("conv_gemm_kernel");
+  return MGLD_OK;
+}
+
+// ---- split-K path: pass 1 = raw fp32 partial tiles into workspace slabs, pass 2 = deterministic sum + epilogue ---------
+static bool split_plan(const mgld_conv_gemm_desc* d, int* S, int* bn, size_t* bytes, int* ldws, int* slab_frames) {
+  if (d->out_f32 || d->stats_out) return false;
+  const bool pair = d->epilogue == MGLD_EPI_GEGLU || d->epilogue == MGLD_EPI_SPADE;
+  int BW, BH, BT;
+  pick_box(d->T, d->H, d->W, &BW, &BH, &BT);
+  const int tiles_m = ceil_div(d->W, BW) * ceil_div(d->H, BH) * ceil_div(d->T, BT);
+  const int ntaps = d->taps == MGLD_TAPS_5X1 ? 5 : d->taps;
+  const int num_k = ntaps * ceil_div(d->C1 + d->C2, 64);
+  const int block_n = pair ? 128 : (d->N % 128 == 0 ? 128 : (d->N % 64 == 0 ? 64 : 0));
+  if (!block_n) return false;
+  int s = pick_split_k(tiles_m * (d->N / block_n), num_k, num_sms());
+  while (s > 1 && (s - 1) * ceil_div(num_k, s) >= num_k) --s;   // every K-slice must be non-empty
+  if (s <= 1) return false;
+  *S = s; *bn = block_n;
+  *ldws = d->N;                                        // raw accumulator columns (multiple of 64)
+  *slab_frames = ceil_div(d->T, BT) * BT;              // frames padded to whole boxes: slabs never overlap
+  *bytes = (size_t)s * *slab_frames * d->H * d->W * *ldws * sizeof(float);
+  return true;
+}
+
+extern "C" long long mgld_conv_gemm_workspace_bytes(const mgld_conv_gemm_desc* d) {
+  int S, bn, ldws, sf;
+  size_t bytes;
+  if (!d || !initialised() || !split_plan(d, &S, &bn, &bytes, &ldws, &sf)) return 0;
+  return (long long)bytes;
+}
+
+extern "C" int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream_) {
+  if (!initialised()) { set_error("mgld_init() has not been called"); return MGLD_ERR_NOT_INIT; }
+  MGLD_CHECK_ARG(d && d->a && d->w && d->out, "conv_gemm: null pointer");
+  int S, bn, ldws, sf;
+  size_t bytes;
+  if (!d->workspace || !split_plan(d, &S, &bn, &bytes, &ldws, &sf) || (size_t)d->workspace_bytes < bytes)
+    return conv_gemm_single(d, stream_, 1, 0);
+  // pass 1: raw partial sums.  The descriptor is rewritten to a plain fp32-output GEMM into the workspace.
+  mgld_conv_gemm_desc r = *d;
+  r.epilogue = MGLD_EPI_LINEAR; r.act = MGLD_ACT_NONE; r.bias = nullptr; r.alpha = 1.f; r.beta = 0.f; r.res = nullptr;
+  r.h = nullptr; r.gn_stats = nullptr; r.out = d->workspace; r.ldout = ldws; r.out_col0 = 0; r.out_f32 = 1; r.block_n = bn;
+  int rc = conv_gemm_single(&r, stream_, S, sf);
+  if (rc) return rc;
+  SplitFinalizeParams f;
+  memset(&f, 0, sizeof(f));
+  f.ws = reinterpret_cast<const float*>(d->workspace);
+  f.slab_stride = (long long)sf * d->H * d->W * ldws;
+  f.S = S; f.T = d->T; f.H = d->H; f.W = d->W; f.ldws = ldws;
+  f.N = d->N; f.epilogue = d->epilogue; f.act = d->act; f.bias = d->bias; f.alpha = d->alpha; f.beta = d->beta;
+  f.n_out_total = (d->epilogue == MGLD_EPI_LINEAR) ? d->N : d->N / 2;
+  f.res = reinterpret_cast<const __half*>(d->res); f.ldres = d->ldres;
+  f.h = reinterpret_cast<const __half*>(d->h); f.ldh = d->ldh;
+  f.gn_stats = d->gn_stats; f.gn_weight = d->gn_weight; f.gn_bias = d->gn_bias; f.groups = d->groups;
+  f.ch_per_group = d->groups > 0 ? f.n_out_total / d->groups : 1;
+  f.out = reinterpret_cast<__half*>(d->out); f.ldout = d->ldout; f.out_col0 = d->out_col0;
+  MGLD_CHECK_ARG(f.n_out_total % 8 == 0, "conv_gemm(split-K): output columns must be a multiple of 8");
+  const long long total = (long long)d->T * d->H * d->W * (f.n_out_total / 8);
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  splitk_finalize_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(f);
+  MGLD_LAUNCH_CHECK("splitk_finalize_kernel");
   return MGLD_OK;
 }

@@ -94,16 +94,16 @@ constexpr int kScPix = 32;
 __global__ void conv_small_cin_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                       const float* __restrict__ bias, __half* __restrict__ out, int N, int Cin, int H,
                                       int W, int Cout, int ks, int ldo) {
-  __shared__ float patch[kScPix][73];
+  __shared__ __align__(16) float patch[kScPix][76];   // 72 taps max, padded to float4 rows
   const int K = Cin * ks * ks, pad = ks / 2;
   const long long total = static_cast<long long>(N) * H * W;
   const long long p0 = static_cast<long long>(blockIdx.x) * kScPix;
   const int co = blockIdx.y * 128 + threadIdx.x;
-  for (int i = threadIdx.x; i < kScPix * K; i += blockDim.x) {
-    const int pp = i / K, k = i - pp * K;
+  for (int i = threadIdx.x; i < kScPix * 76; i += blockDim.x) {
+    const int pp = i / 76, k = i - pp * 76;
     const long long p = p0 + pp;
     float v = 0.f;
-    if (p < total) {
+    if (p < total && k < K) {
       const int x = p % W, y = (p / W) % H, n = p / (static_cast<long long>(W) * H);
       const int c = k / (ks * ks), ky = (k / ks) % ks, kx = k % ks;
       const int iy = y + ky - pad, ix = x + kx - pad;
@@ -117,13 +117,22 @@ __global__ void conv_small_cin_kernel(const float* __restrict__ in, const float*
 #pragma unroll
   for (int k = 0; k < 72; ++k) wr[k] = k < K ? __ldg(w + static_cast<long long>(co) * K + k) : 0.f;
   const float b = bias ? __ldg(bias + co) : 0.f;
+  const int K4 = (K + 3) >> 2;
   for (int pp = 0; pp < kScPix; ++pp) {
     const long long p = p0 + pp;
     if (p >= total) break;
     float acc = b;
+    // one 16-byte broadcast read feeds 4 FMAs (the patch is shared by all 128 channels of the block)
 #pragma unroll
-    for (int k = 0; k < 72; ++k)
-      if (k < K) acc = fmaf(patch[pp][k], wr[k], acc);
+    for (int k4 = 0; k4 < 18; ++k4) {
+      if (k4 < K4) {
+        const float4 pv = *reinterpret_cast<const float4*>(&patch[pp][k4 * 4]);
+        acc = fmaf(pv.x, wr[k4 * 4], acc);
+        acc = fmaf(pv.y, wr[k4 * 4 + 1], acc);
+        acc = fmaf(pv.z, wr[k4 * 4 + 2], acc);
+        acc = fmaf(pv.w, wr[k4 * 4 + 3], acc);
+      }
+    }
     out[p * ldo + co] = __float2half_rn(acc);
   }
 }

@@ -131,10 +131,6 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, int ld1, 
     const long long m = static_cast<long long>(t) * HW + r;
     float f[8];
     unpack8(load_cat8(x1, C1, ld1, x2, ld2, m, v * 8), f);
-    // a vector of 8 channels touches at most two groups (cpg >= 4): [0, nb) in g, the rest in g + 1
-    const int g = (v * 8) / cpg, nb = (g + 1) * cpg - v * 8;
-    const float m0 = sh[2 * g], r0s = sh[2 * g + 1];
-    const float m1 = nb < 8 ? sh[2 * g + 2] : 0.f, r1s = nb < 8 ? sh[2 * g + 3] : 0.f;
     float gm[8], bt[8];
     if (gamma) {
       const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), gb = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
@@ -142,9 +138,20 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, int ld1, 
       gm[0] = ga.x; gm[1] = ga.y; gm[2] = ga.z; gm[3] = ga.w; gm[4] = gb.x; gm[5] = gb.y; gm[6] = gb.z; gm[7] = gb.w;
       bt[0] = ba.x; bt[1] = ba.y; bt[2] = ba.z; bt[3] = ba.w; bt[4] = bb.x; bt[5] = bb.y; bt[6] = bb.z; bt[7] = bb.w;
     }
+    if (cpg >= 4) {
+      // a vector of 8 channels touches at most two groups: [0, nb) in g, the rest in g + 1
+      const int g = (v * 8) / cpg, nb = (g + 1) * cpg - v * 8;
+      const float m0 = sh[2 * g], r0s = sh[2 * g + 1];
+      const float m1 = nb < 8 ? sh[2 * g + 2] : 0.f, r1s = nb < 8 ? sh[2 * g + 3] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = i < nb ? (f[i] - m0) * r0s : (f[i] - m1) * r1s;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const int g = (v * 8 + i) / cpg; f[i] = (f[i] - sh[2 * g]) * sh[2 * g + 1]; }
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float y = i < nb ? (f[i] - m0) * r0s : (f[i] - m1) * r1s;
+      float y = f[i];
       if (gamma) y = fmaf(y, gm[i], bt[i]);
       if (silu) y = y / (1.f + __expf(-y));
       f[i] = y;

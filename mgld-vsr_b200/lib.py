@@ -37,6 +37,7 @@ class ConvGemmDesc(ctypes.Structure):
         ("out", ctypes.c_void_p), ("ldout", ctypes.c_int32), ("out_col0", ctypes.c_int32),
         ("out_f32", ctypes.c_int32),
         ("stats_out", ctypes.c_void_p), ("stats_groups", ctypes.c_int32),
+        ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64),
     ]
 
 
@@ -51,6 +52,7 @@ def load():
     lib = ctypes.CDLL(LIB_PATH)
     lib.mgld_last_error.restype = ctypes.c_char_p
     lib.mgld_abi_version.restype = ctypes.c_int
+    lib.mgld_conv_gemm_workspace_bytes.restype = ctypes.c_longlong
     _lib = lib
     return lib
 

@@ -47,6 +47,9 @@ def interleave_pair(wa, wb, blk=64):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+SPLIT_K = True          # let layers with too few tiles use the split-K path (needs a workspace, allocated here)
+
+
 def conv_gemm(a, w, *, taps=TAPS_1, a2=None, bias=None, epilogue=EPI_LINEAR, act=ACT_NONE, alpha=1.0, beta=0.0,
               res=None, h=None, gn_stats=None, gn_weight=None, gn_bias=None, groups=32, out=None, out_col0=0,
               out_f32=False, block_n=0, stats_out=None, stats_groups=32):
@@ -104,6 +107,12 @@ def conv_gemm(a, w, *, taps=TAPS_1, a2=None, bias=None, epilogue=EPI_LINEAR, act
     if stats_out is not None:
         assert stats_out.dtype == torch.float64 and stats_out.shape == (T, stats_groups, 2) and stats_out.is_contiguous()
         d.stats_out, d.stats_groups = stats_out.data_ptr(), stats_groups
+    if SPLIT_K:
+        need = _L.lib().mgld_conv_gemm_workspace_bytes(ctypes.byref(d))
+        if need > 0:
+            ws = torch.empty(need, device=a.device, dtype=torch.uint8)   # caching allocator; graph-capture safe
+            d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+            _count(1)
     _count(1)
     _L.check(_L.lib().mgld_conv_gemm(ctypes.byref(d), _L.stream_ptr()))
     return out

@@ -72,6 +72,37 @@ def test_conv_strided_views_and_column_offset():
     assert torch.equal(buf[..., C + 96:], ref_buf[..., C + 96:])     # untouched slots stay zero
 
 
+def test_split_k_path():
+    """few output tiles + long K -> partial fp32 tiles + deterministic finalize; must equal the single-pass result"""
+    O = ops()
+    T, H, W, C = 5, 8, 8, 1280
+    x, res = rnd(T, H, W, C).half(), rnd(T, H, W, C).half()
+    w, b = O.pack_conv_weight(rnd(C, C, 3, 3, scale=(9 * C) ** -0.5)), rnd(C)
+    kw = dict(taps=9, bias=b, act=O.ACT_SILU, res=res, alpha=0.5, beta=2.0)
+    O.SPLIT_K = False
+    single = O.conv_gemm(x, w, **kw)
+    O.SPLIT_K = True
+    n0 = O.LAUNCHES[0]
+    split = O.conv_gemm(x, w, **kw)
+    assert O.LAUNCHES[0] - n0 == 2, "this shape is expected to take the split-K path (2 launches)"
+    assert rel_err(split, E.conv_gemm(x, w, **kw)) < 4e-3 and rel_err(split, single) < 2e-3
+    again = O.conv_gemm(x, w, **kw)
+    assert torch.equal(split, again)                              # fixed summation order: bitwise reproducible
+    # pair epilogues through the finalize kernel
+    a = rnd(320, 1280).half()
+    wf, bf = rnd(1280, 1280, scale=1280 ** -0.5).half(), rnd(1280)
+    wp, bp = O.interleave_pair(wf[:640], wf[640:]), O.interleave_pair(bf[:640], bf[640:])
+    y = a.float() @ wf.float().t() + bf
+    assert rel_err(O.conv_gemm(a, wp, bias=bp, epilogue=O.EPI_GEGLU), y[:, :640] * F.gelu(y[:, 640:])) < 4e-3
+    actv, h = rnd(T, H, W, 128).half(), rnd(T, H, W, 640).half()
+    wg, wb = O.pack_conv_weight(rnd(640, 128, 3, 3, scale=0.03)), O.pack_conv_weight(rnd(640, 128, 3, 3, scale=0.03, seed=5))
+    st = O.gn_finalize(O.gn_stats(h), H * W, 640, 1e-5)
+    kw = dict(taps=9, bias=O.interleave_pair(rnd(640, scale=0.1), rnd(640, scale=0.1, seed=3)), epilogue=O.EPI_SPADE, h=h,
+              gn_stats=st, gn_weight=rnd(640, seed=7), gn_bias=rnd(640, seed=9), groups=32, res=rnd(T, H, W, 640).half(), beta=1.0)
+    wp = O.interleave_pair(wg, wb)
+    assert rel_err(O.conv_gemm(actv, wp, **kw), E.conv_gemm(actv, wp, **kw)) < 4e-3
+
+
 @pytest.mark.parametrize("T,H,W,Ci,Co,taps,res", [(5, 64, 64, 320, 320, 9, False), (5, 8, 8, 1280, 1280, 9, True),
                                                   (5, 1, 1024, 640, 640, 1, True), (3, 30, 46, 128, 256, 9, False),
                                                   (5, 16, 16, 256, 128, 9, False)])
