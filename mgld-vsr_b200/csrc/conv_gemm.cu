@@ -29,7 +29,7 @@ constexpr int kKChunk = 64;  // fp16 elements per K step = one 128-byte swizzle 
 constexpr int kABytes = kBlockM * kKChunk * 2;
 constexpr int kPanelBytes = kBlockM * 128;  // one staging panel: 128 rows x 128 bytes (64 fp16 or 32 fp32 columns)
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
+constexpr int kThreads = 256;   // warp 0: A producer, 1: MMA, 2-5: epilogue, 6-7: B producers (half tile each)
 
 struct ConvGemmParams {
   int T, H, W;
@@ -190,7 +190,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&full_bar[s]), 3);   // three producer threads (A, B lower half, B upper half)
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -238,10 +238,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
           const uint32_t fb = smem_u32(&full_bar[s]);
           const uint32_t sa = smem_base + s * stage_bytes;
-          mbar_expect_tx(fb, stage_bytes);
+          mbar_expect_tx(fb, kABytes);
           if (kc < p.kchunks1) tma_load_4d(sa, &tmA, fb, kc * kKChunk, x0 + dx, y0 + dy, t0 + dt);
           else tma_load_4d(sa, &tmA2, fb, (kc - p.kchunks1) * kKChunk, x0 + dx, y0 + dy, t0 + dt);
-          tma_load_2d(sa + kABytes, &tmB, fb, k * kKChunk, n0);
         }
         if (p.has_res || pair_spade) {
           // residual (and SPADE's h) tile of THIS output tile, into the staging buffers the epilogue will overwrite
@@ -281,6 +280,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           umma_commit(smem_u32(&empty_bar[s]));
         }
         umma_commit(smem_u32(&acc_full[buf]));
+      }
+    }
+  } else if (warp >= 6) {
+    // ============================ B (weight) producers: one TMA-issuing thread per half tile ============================
+    // A single thread sustains only ~46 B/clk of 16 KB TMA boxes (tools/microbench/tma_fill2.cu); three issuing threads
+    // (A + two B halves) lift the per-SM fill rate towards the ~100 B/clk the SM can ingest.
+    if (lane == 0) {
+      const int half = warp - 6;
+      const int hrows = p.block_n >> 1;
+      const int hbytes = hrows * kKChunk * 2;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int x0, y0, t0, nt;
+        tile_coords(tile, x0, y0, t0, nt);
+        const int n0 = nt * p.block_n + half * hrows;
+        const int kb = (tile % p.split_k) * p.k_per_split, ke = min(kb + p.k_per_split, num_k);
+        for (int k = kb; k < ke; ++k, ++it) {
+          const int s = it % p.stages;
+          mbar_wait(smem_u32(&empty_bar[s]), ((it / p.stages) & 1) ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          mbar_expect_tx(fb, hbytes);
+          tma_load_2d(smem_base + s * stage_bytes + kABytes + half * hbytes, &tmB, fb, k * kKChunk, n0);
+        }
       }
     }
   } else {
@@ -518,16 +540,20 @@ __global__ void splitk_finalize_kernel(const SplitFinalizeParams p) {
   }
 }
 
-// split-K plan: only when a single pass would leave most SMs idle and K is long enough to amortise the second pass
+// split-K plan.  The mainloop of one CTA is bound by its SM's L2->SMEM fill rate (~50 B/clk), so a layer's time is
+// ~ waves x (K chunks per unit); splitting K helps whenever it shortens that product by more than the price of the second
+// (finalize) pass, which is about 10 chunk-times.  Short-K GEMMs (1x1 / linear layers) never split.
 static int pick_split_k(int tiles, int num_k, int sms) {
-  if (tiles * 10 >= sms * 6 || num_k < 16) return 1;
+  if (num_k < 48) return 1;
+  const double fin = 10.0;
+  double best_cost = (double)((tiles + sms - 1) / sms) * num_k;
   int best = 1;
-  double best_util = (double)tiles / sms;
   for (int S = 2; S <= 8; ++S) {
-    if (num_k / S < 8) break;
+    const int kper = (num_k + S - 1) / S;
+    if (kper < 12) break;
     const int units = tiles * S;
-    const double util = (double)units / ((double)((units + sms - 1) / sms) * sms);
-    if (util > best_util * 1.08) { best_util = util; best = S; }
+    const double cost = (double)((units + sms - 1) / sms) * kper + fin;
+    if (cost < best_cost * 0.85) { best_cost = cost; best = S; }
   }
   return best;
 }
@@ -668,7 +694,7 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
     const uint64_t K = (uint64_t)ntaps * (d->C1 + d->C2);
     uint64_t dimsB[2] = {K, (uint64_t)d->N};
     uint64_t strB[1] = {K * 2};
-    uint32_t boxB[2] = {64, (uint32_t)p.block_n};
+    uint32_t boxB[2] = {64, (uint32_t)(p.block_n / 2)};   // each of the two B-producer threads loads half of the N tile
     rc = make_tmap_f16(&tmB, d->w, 2, dimsB, strB, boxB);
     if (rc) return rc;
     if (d->out_f32) {
