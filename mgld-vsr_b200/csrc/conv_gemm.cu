@@ -29,7 +29,7 @@ constexpr int kKChunk = 64;  // fp16 elements per K step = one 128-byte swizzle 
 constexpr int kABytes = kBlockM * kKChunk * 2;
 constexpr int kPanelBytes = kBlockM * 128;  // one staging panel: 128 rows x 128 bytes (64 fp16 or 32 fp32 columns)
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 256;   // warp 0: A producer, 1: MMA, 2-5: epilogue, 6-7: B producers (half tile each)
+constexpr int kThreads = 256;   // warp 0: A producer, 1: MMA, 2-5: epilogue, 6-7: B producers
 
 struct ConvGemmParams {
   int T, H, W;
@@ -42,6 +42,7 @@ struct ConvGemmParams {
   int stages, tmem_cols, acc_stride;
   int panel_cols;  // fp16 output columns per staging panel: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B)
   int epilogue, act, has_res, out_f32;
+  int cta_pair;  // 1: launched as clusters of 2; one cta_group::2 MMA computes the two M tiles of a pair, each CTA stages half of B
   const float* bias;
   float alpha, beta;
   const float* gn_stats;
@@ -51,6 +52,7 @@ struct ConvGemmParams {
   double* stats_out;      // optional fused GroupNorm statistics of the OUTPUT: [T, stat_groups, 2] (sum, sumsq), accumulated
   int stat_groups, stat_cpg;
   uint32_t off_staging, off_hstage, off_bias, off_stats;  // byte offsets from the 1024-aligned smem base
+  long long* dbg;  // optional per-CTA cycle counters [grid][8] (mgld_conv_gemm_set_debug_counters); null in production
 };
 
 __device__ __forceinline__ void act_inplace32(float* v, int act) {
@@ -165,6 +167,9 @@ struct StatAcc {
   }
 };
 
+// kPair instantiation must be launched as clusters of 2 (a kernel containing cta_group::2 instructions cannot be launched
+// without a cluster: cudaErrorInvalidClusterSize), hence two instantiations rather than a runtime flag.
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
@@ -180,9 +185,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const int stage_bytes = kABytes + p.block_n * kKChunk * 2;
+  // CTA pair: the two CTAs of a cluster own M tiles 2j and 2j+1 of the same N tile.  Each stages its own A rows and
+  // block_n/2 rows of the weight tile; the leader's MMA thread issues cta_group::2 MMAs (M = 256) that read both CTAs'
+  // shared memory and write both CTAs' TMEM.  L2 -> SM traffic per MMA flop drops by (128+bn/2)/(128+bn).
+  constexpr bool pair = kPair;
+  const int cs = pair ? 2 : 1;
+  uint32_t rank = 0;
+  if constexpr (pair) rank = cluster_ctarank();
+  const int worker = blockIdx.x / cs, nworkers = gridDim.x / cs;
+  const int tiles_mw = (p.tiles_m + cs - 1) / cs;
+  const int b_rows = p.block_n / cs;                      // weight rows staged by THIS CTA
+  const int stage_bytes = kABytes + b_rows * kKChunk * 2;
   const int num_k = p.taps * p.kchunks;
-  const int total_tiles = p.tiles_m * p.tiles_n * p.split_k;  // work units
+  const int total_units = tiles_mw * p.tiles_n * p.split_k;  // work units of a worker (CTA or CTA pair)
   const bool pair_spade = p.epilogue == MGLD_EPI_SPADE;
 
   if (threadIdx.x == 0) {
@@ -190,57 +205,90 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 3);   // three producer threads (A, B lower half, B upper half)
+      mbar_init(smem_u32(&full_bar[s]), 1);   // one arrival (A producer; the pair leader's) carrying the stage's whole tx count
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&acc_full[b]), 1);
-      mbar_init(smem_u32(&acc_empty[b]), 128);
+      mbar_init(smem_u32(&acc_empty[b]), 128 * cs);
     }
     mbar_init(smem_u32(&res_full), 1);
     mbar_init(smem_u32(&staging_free), 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), p.tmem_cols);
+  if (warp == 1) {
+    if constexpr (pair) tmem_alloc_pair(smem_u32(&tmem_base_slot), p.tmem_cols);
+    else tmem_alloc(smem_u32(&tmem_base_slot), p.tmem_cols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (pair) cluster_sync_all();   // barrier inits visible to the peer before any remote arrive / TMA completion
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
   // tile -> coordinates; consecutive tiles share the weight tile (n) and walk the pixel boxes (L2-friendly)
-  auto tile_coords = [&](int unit, int& x0, int& y0, int& t0, int& nt) {
-    const int tile = unit / p.split_k;   // the splits of one tile run on neighbouring CTAs
-    const int tm = tile % p.tiles_m;
-    nt = tile / p.tiles_m;
+  // returns false for the padding M tile of an odd tile count (pair mode): its box lies beyond T, loads are zero-filled
+  auto tile_coords = [&](int unit, int& x0, int& y0, int& t0, int& nt) -> bool {
+    const int tile = unit / p.split_k;   // the splits of one tile run on neighbouring workers
+    const int tm = (tile % tiles_mw) * cs + static_cast<int>(rank);
+    nt = tile / tiles_mw;
     x0 = (tm % p.tiles_w) * p.BW;
     y0 = ((tm / p.tiles_w) % p.tiles_h) * p.BH;
     t0 = (tm / (p.tiles_w * p.tiles_h)) * p.BT;
+    return tm < p.tiles_m;
   };
 
   if (warp == 0) {
     // ============================ TMA producer ============================
-    if (lane == 0) {
-      int it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    // The three single-thread loops (this one, the MMA issuer, the B producers) are latency chains of scalar
+    // instructions: ~110 dependent instructions per K chunk (runtime divisions, S2UR address rebuilds, parameter reloads)
+    // cost ~800 cycles and WERE the mainloop bound.  So: all loop state is carried incrementally in registers.
+    if (elect_one()) {
+      int lt = 0;
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t sa = smem_base;
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      uint32_t full0_lead = full0;
+      if constexpr (pair) full0_lead = mapa_shared(full0, 0);
+      const int stages = p.stages, kchunks = p.kchunks, kchunks1 = p.kchunks1, tap_mode = p.tap_mode;
+      const uint32_t stage_tx = cs * stage_bytes;
+      long long dbg_wait = 0;
+      const long long dbg_t0 = p.dbg ? clock64() : 0;
+      for (int tile = worker; tile < total_units; tile += nworkers, ++lt) {
         int x0, y0, t0, nt;
         tile_coords(tile, x0, y0, t0, nt);
-        const int n0 = nt * p.block_n;
         const int kb = (tile % p.split_k) * p.k_per_split, ke = min(kb + p.k_per_split, num_k);
-        for (int k = kb; k < ke; ++k, ++it) {
-          const int tap = k / p.kchunks, kc = k - tap * p.kchunks;
-          int dx = 0, dy = 0, dt = 0;
-          if (p.tap_mode == MGLD_TAPS_3X3) { dx = tap % 3 - 1; dy = tap / 3 - 1; }
-          else if (p.tap_mode == MGLD_TAPS_T3) { dt = tap - 1; }
-          else if (p.tap_mode == MGLD_TAPS_1X5) { dx = tap - 2; }
-          else if (p.tap_mode == MGLD_TAPS_5X1) { dy = tap - 2; }
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
-          const uint32_t fb = smem_u32(&full_bar[s]);
-          const uint32_t sa = smem_base + s * stage_bytes;
-          mbar_expect_tx(fb, kABytes);
-          if (kc < p.kchunks1) tma_load_4d(sa, &tmA, fb, kc * kKChunk, x0 + dx, y0 + dy, t0 + dt);
-          else tma_load_4d(sa, &tmA2, fb, (kc - p.kchunks1) * kKChunk, x0 + dx, y0 + dy, t0 + dt);
+        int tap = kb / kchunks, kc = kb - tap * kchunks;
+        int cx = x0, cy = y0, ct = t0;   // box origin of the current tap
+        auto set_tap = [&](int tp) {
+          cx = x0; cy = y0; ct = t0;
+          if (tap_mode == MGLD_TAPS_3X3) { cx += tp % 3 - 1; cy += tp / 3 - 1; }
+          else if (tap_mode == MGLD_TAPS_T3) { ct += tp - 1; }
+          else if (tap_mode == MGLD_TAPS_1X5) { cx += tp - 2; }
+          else if (tap_mode == MGLD_TAPS_5X1) { cy += tp - 2; }
+        };
+        set_tap(tap);
+        for (int k = kb; k < ke; ++k) {
+          if (p.dbg) {
+            const long long tw = clock64();
+            mbar_wait(empty0 + 8 * s, ph ^ 1);
+            dbg_wait += clock64() - tw;
+          } else {
+            mbar_wait(empty0 + 8 * s, ph ^ 1);
+          }
+          // the stage's whole transaction count (A + B, of both CTAs of a pair) rides on this one arrival; the B
+          // producers only issue.  Their bytes may land first (tx count transiently negative) - the phase cannot
+          // complete before the pending arrival, and nobody issues into a stage before its empty barrier fired.
+          if (rank == 0) mbar_expect_tx(full0 + 8 * s, stage_tx);
+          const bool src1 = kc < kchunks1;
+          const CUtensorMap* tm = src1 ? &tmA : &tmA2;
+          const int c0 = (src1 ? kc : kc - kchunks1) * kKChunk;
+          if constexpr (pair) tma_load_4d_pair(sa, tm, full0_lead + 8 * s, c0, cx, cy, ct);
+          else tma_load_4d(sa, tm, full0 + 8 * s, c0, cx, cy, ct);
+          if (++kc == kchunks) { kc = 0; set_tap(++tap); }
+          sa += stage_bytes;
+          if (++s == stages) { s = 0; ph ^= 1; sa = smem_base; }
         }
         if (p.has_res || pair_spade) {
           // residual (and SPADE's h) tile of THIS output tile, into the staging buffers the epilogue will overwrite
@@ -255,53 +303,88 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (pair_spade) tma_load_4d(smem_base + p.off_hstage, &tmH, rb, c0, x0, y0, t0);
         }
       }
+      if (p.dbg) { p.dbg[blockIdx.x * 8 + 0] = dbg_wait; p.dbg[blockIdx.x * 8 + 1] = clock64() - dbg_t0; }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(kBlockM, p.block_n, 0, 0);
-      int it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc = umma_idesc_f16(kBlockM * cs, p.block_n, 0, 0);
+      int lt = 0;
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      const int stages = p.stages;
+      // descriptors differ only in the 14-bit (address >> 4) field: carry that field incrementally
+      const uint64_t desc0 = umma_smem_desc(smem_base, 0, 1024, kSwz128);
+      const uint32_t desc_step = stage_bytes >> 4;
+      uint64_t adesc = desc0;
+      long long dbg_wf = 0, dbg_wa = 0;
+      const long long dbg_t0 = p.dbg ? clock64() : 0;
+      for (int tile = worker; tile < total_units; tile += nworkers, ++lt) {
         const int buf = lt & 1;
+        const long long twa = p.dbg ? clock64() : 0;
         mbar_wait(smem_u32(&acc_empty[buf]), ((lt >> 1) & 1) ^ 1);
+        if (p.dbg) dbg_wa += clock64() - twa;
         tc_fence_after();
         const uint32_t dcol = tmem_base + buf * p.acc_stride;
         const int kb = (tile % p.split_k) * p.k_per_split, ke = min(kb + p.k_per_split, num_k);
-        for (int k = kb; k < ke; ++k, ++it) {
-          const int s = it % p.stages;
-          mbar_wait(smem_u32(&full_bar[s]), (it / p.stages) & 1);
+        for (int k = kb; k < ke; ++k) {
+          if (p.dbg) {
+            const long long tw = clock64();
+            mbar_wait(full0 + 8 * s, ph);
+            dbg_wf += clock64() - tw;
+          } else {
+            mbar_wait(full0 + 8 * s, ph);
+          }
           tc_fence_after();
-          const uint32_t sa = smem_base + s * stage_bytes;
-          const uint64_t adesc = umma_smem_desc(sa, 0, 1024, kSwz128);
-          const uint64_t bdesc = umma_smem_desc(sa + kABytes, 0, 1024, kSwz128);
+          const uint64_t bdesc = adesc + (kABytes >> 4);
+          if constexpr (pair) {
 #pragma unroll
-          for (int kk = 0; kk < kKChunk / 16; ++kk)
-            umma_ss(dcol, adesc + 2 * kk, bdesc + 2 * kk, idesc, ((k - kb) | kk) != 0);  // +32 B along K per step
-          umma_commit(smem_u32(&empty_bar[s]));
+            for (int kk = 0; kk < kKChunk / 16; ++kk)
+              umma_ss_pair(dcol, adesc + 2 * kk, bdesc + 2 * kk, idesc, ((k - kb) | kk) != 0);
+            umma_commit_pair(empty0 + 8 * s, 3);   // frees the stage in both CTAs
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < kKChunk / 16; ++kk)
+              umma_ss(dcol, adesc + 2 * kk, bdesc + 2 * kk, idesc, ((k - kb) | kk) != 0);  // +32 B along K per step
+            umma_commit(empty0 + 8 * s);
+          }
+          adesc += desc_step;
+          if (++s == stages) { s = 0; ph ^= 1; adesc = desc0; }
         }
-        umma_commit(smem_u32(&acc_full[buf]));
+        if constexpr (pair) umma_commit_pair(smem_u32(&acc_full[buf]), 3);
+        else umma_commit(smem_u32(&acc_full[buf]));
       }
+      if (p.dbg) { p.dbg[blockIdx.x * 8 + 2] = dbg_wf; p.dbg[blockIdx.x * 8 + 3] = dbg_wa; p.dbg[blockIdx.x * 8 + 4] = clock64() - dbg_t0; }
     }
   } else if (warp >= 6) {
-    // ============================ B (weight) producers: one TMA-issuing thread per half tile ============================
-    // A single thread sustains only ~46 B/clk of 16 KB TMA boxes (tools/microbench/tma_fill2.cu); three issuing threads
-    // (A + two B halves) lift the per-SM fill rate towards the ~100 B/clk the SM can ingest.
-    if (lane == 0) {
-      const int half = warp - 6;
+    // ============================ B (weight) producers ============================
+    // The tensor map's box is block_n/2 rows.  Single CTA: warps 6 and 7 each load one half (a TMA-issuing thread manages
+    // one op per ~270 cycles, tools/microbench/tma_fill4.cu).  CTA pair: warp 6 loads this CTA's half, warp 7 idles.
+    if (!(pair && warp == 7) && elect_one()) {
+      const int half = pair ? static_cast<int>(rank) : warp - 6;
       const int hrows = p.block_n >> 1;
       const int hbytes = hrows * kKChunk * 2;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int slot = pair ? 0 : half;   // position of the half inside this CTA's B stage
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      uint32_t full0_lead = full0;
+      if constexpr (pair) full0_lead = mapa_shared(full0, 0);
+      const int stages = p.stages;
+      const uint32_t dst0 = smem_base + kABytes + slot * hbytes;
+      uint32_t dst = dst0;
+      for (int tile = worker; tile < total_units; tile += nworkers) {
         int x0, y0, t0, nt;
         tile_coords(tile, x0, y0, t0, nt);
         const int n0 = nt * p.block_n + half * hrows;
         const int kb = (tile % p.split_k) * p.k_per_split, ke = min(kb + p.k_per_split, num_k);
-        for (int k = kb; k < ke; ++k, ++it) {
-          const int s = it % p.stages;
-          mbar_wait(smem_u32(&empty_bar[s]), ((it / p.stages) & 1) ^ 1);
-          const uint32_t fb = smem_u32(&full_bar[s]);
-          mbar_expect_tx(fb, hbytes);
-          tma_load_2d(smem_base + s * stage_bytes + kABytes + half * hbytes, &tmB, fb, k * kKChunk, n0);
+        for (int k = kb; k < ke; ++k) {
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          if constexpr (pair) tma_load_2d_pair(dst, &tmB, full0_lead + 8 * s, k * kKChunk, n0);
+          else tma_load_2d(dst, &tmB, full0 + 8 * s, k * kKChunk, n0);
+          dst += stage_bytes;
+          if (++s == stages) { s = 0; ph ^= 1; dst = dst0; }
         }
       }
     }
@@ -315,9 +398,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float* bias_s = reinterpret_cast<float*>(smem_gen + p.off_bias);
     float* stat_s = reinterpret_cast<float*>(smem_gen + p.off_stats);
     int lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    long long dbg_we = 0;
+    const long long dbg_t0e = p.dbg ? clock64() : 0;
+    for (int tile = worker; tile < total_units; tile += nworkers, ++lt) {
       int x0, y0, t0, nt;
-      tile_coords(tile, x0, y0, t0, nt);
+      const bool tile_valid = tile_coords(tile, x0, y0, t0, nt);
       const int buf = lt & 1;
       const int n0 = nt * p.block_n;
       // bias tile -> smem (all threads passed the previous tile's closing barrier, so bias_s is free)
@@ -330,7 +415,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool valid = (x0 + r_x < p.W) && (y0 + r_y < p.H) && (t0 + r_t < p.T);
         sa.begin(nt * p.n_out_tile, p.stat_cpg, (nt * p.n_out_tile) / p.stat_cpg, (q * 32) / (p.BW * p.BH), stat_s, valid, lane);
       }
+      const long long twe = (p.dbg && e == 0) ? clock64() : 0;
       mbar_wait(smem_u32(&acc_full[buf]), (lt >> 1) & 1);
+      if (p.dbg && e == 0) dbg_we += clock64() - twe;
       tc_fence_after();
       if (p.has_res || pair_spade) mbar_wait(smem_u32(&res_full), lt & 1);
       named_bar_sync(1, 128);
@@ -409,7 +496,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       // accumulator buffer drained -> the MMA warp may start tile lt+2 in it
       tc_fence_before();
-      mbar_arrive(smem_u32(&acc_empty[buf]));
+      if (!pair || rank == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+      else mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[buf]), 0));   // the pair's MMA issuer lives in the leader
       if (p.stats_out) sa.flush();
       // staging tile complete -> one thread issues the TMA stores
       fence_proxy_async_smem();
@@ -428,7 +516,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int cols_per_panel = p.out_f32 ? 32 : p.panel_cols;
         const int pbytes = (!p.out_f32 && p.panel_cols == 32) ? kPanelBytes / 2 : kPanelBytes;
         for (int pn = 0; pn < p.n_panels; ++pn) {
-          if (c0 + pn * cols_per_panel < p.n_out_total)
+          if (tile_valid && c0 + pn * cols_per_panel < p.n_out_total)
             tma_store_4d(&tmOut, smem_base + p.off_staging + pn * pbytes, c0 + pn * cols_per_panel, x0, y0,
                          t0 + (tile % p.split_k) * p.slab_frames);
         }
@@ -439,13 +527,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       named_bar_sync(1, 128);
     }
     if (e == 0) tma_store_wait_all();
+    if (p.dbg && e == 0) { p.dbg[blockIdx.x * 8 + 5] = dbg_we; p.dbg[blockIdx.x * 8 + 6] = clock64() - dbg_t0e; p.dbg[blockIdx.x * 8 + 7] = lt; }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (pair) cluster_sync_all();   // the peer may still signal this CTA's barriers / read its smem through the MMA
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if constexpr (pair) tmem_dealloc_pair(tmem_base, p.tmem_cols);
+    else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -586,6 +677,14 @@ static void pick_box(int T, int H, int W, int* BW, int* BH, int* BT) {
 }
 
 static bool g_attr_set = false;
+static int g_max_pairs = -1;   // co-resident 2-CTA clusters of conv_gemm_kernel (GPCs with an odd SM count strand one SM)
+
+// CTA-pair mode: MGLD_CONV_PAIR=0 disables, =1 forces (where legal); default: on when both halves of the machine get work
+static long long* g_dbg = nullptr;
+static int pair_mode_env() {
+  const char* e = getenv("MGLD_CONV_PAIR");
+  return e ? atoi(e) : -1;
+}
 
 }  // namespace mgld
 
@@ -633,7 +732,14 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
   p.tap_mode = d->taps;
   p.N = d->N;
   const int sms = num_sms();
-  p.block_n = pair ? 128 : (d->block_n > 0 ? d->block_n : pick_block_n(d->N, p.tiles_m, sms));
+  {
+    const int pm = pair_mode_env();
+    // a pair needs two M tiles; fused statistics keep the single-CTA path
+    p.cta_pair = (p.tiles_m >= 2 && !d->stats_out && pm != 0) ? 1 : 0;
+  }
+  const int workers = p.cta_pair ? sms / 2 : sms;
+  const int tiles_mw = p.cta_pair ? ceil_div(p.tiles_m, 2) : p.tiles_m;
+  p.block_n = pair ? 128 : (d->block_n > 0 ? d->block_n : pick_block_n(d->N, tiles_mw, workers));
   if (d->out_f32 && p.block_n > 128) p.block_n = 128;  // fp32 staging tile: 128 x 128 x 4 B = 64 KB
   MGLD_CHECK_ARG(p.block_n % 32 == 0 && p.block_n >= 32 && p.block_n <= 256, "conv_gemm: block_n=%d", p.block_n);
   p.tiles_n = ceil_div(d->N, p.block_n);
@@ -653,6 +759,7 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
   p.gn_stats = d->gn_stats; p.gn_weight = d->gn_weight; p.gn_bias = d->gn_bias;
   p.groups = d->groups; p.ch_per_group = d->groups > 0 ? p.n_out_total / d->groups : 1;
   p.stats_out = d->stats_out; p.stat_groups = d->stats_groups;
+  p.dbg = g_dbg;
   p.stat_cpg = d->stats_groups > 0 ? p.n_out_total / d->stats_groups : 1;
   if (d->stats_out) {
     MGLD_CHECK_ARG(d->stats_groups > 0 && p.n_out_total % d->stats_groups == 0 && !d->out_f32,
@@ -662,7 +769,7 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
   }
 
   // shared memory plan: [A/B ring][staging panels][h panel (SPADE)][bias]
-  const int stage_bytes = kABytes + p.block_n * 128;
+  const int stage_bytes = kABytes + (p.block_n / (p.cta_pair ? 2 : 1)) * 128;
   const int staging_bytes = d->out_f32 ? p.n_panels * kPanelBytes : p.n_out_tile * kBlockM * 2;
   const int hstage_bytes = d->epilogue == MGLD_EPI_SPADE ? kPanelBytes : 0;
   const int fixed = staging_bytes + hstage_bytes + 1024 /*bias*/ + kStatFrames * kStatGroups * 8 /*stats*/ + 1024 /*alignment slack*/;
@@ -714,12 +821,35 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
   }
 
   if (!g_attr_set) {
-    MGLD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    MGLD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    MGLD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     g_attr_set = true;
   }
-  const int total_tiles = p.tiles_m * p.tiles_n * p.split_k;
-  dim3 grid(total_tiles < sms ? total_tiles : sms, 1, 1);
-  conv_gemm_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmA2, tmB, tmOut, tmRes, tmH, p);
+  const int total_units = tiles_mw * p.tiles_n * p.split_k;
+  if (!p.cta_pair) {
+    dim3 grid(total_units < sms ? total_units : sms, 1, 1);
+    conv_gemm_kernel<false><<<grid, kThreads, smem, stream>>>(tmA, tmA2, tmB, tmOut, tmRes, tmH, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (g_max_pairs < 0) {
+      cfg.gridDim = dim3(2 * (sms / 2), 1, 1);
+      cfg.dynamicSmemBytes = 226 * 1024;
+      int n = 0;
+      MGLD_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<true>, &cfg));
+      g_max_pairs = n > 0 ? (n < sms / 2 ? n : sms / 2) : 1;
+      cfg.dynamicSmemBytes = smem;
+    }
+    const int pairs = total_units < g_max_pairs ? total_units : g_max_pairs;
+    cfg.gridDim = dim3(2 * pairs, 1, 1);
+    MGLD_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, tmA, tmA2, tmB, tmOut, tmRes, tmH, p));
+  }
   MGLD_LAUNCH_CHECK("conv_gemm_kernel");
   return MGLD_OK;
 }
@@ -784,3 +914,8 @@ extern "C" int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream_) {
   MGLD_LAUNCH_CHECK("splitk_finalize_kernel");
   return MGLD_OK;
 }
+
+// Development hook: per-CTA cycle counters of the next conv_gemm launches ([grid][8] int64 in device memory: A-producer
+// wait-on-empty, A-producer total, MMA wait-on-full, MMA wait-on-accumulator, MMA total, epilogue wait, epilogue total,
+// tiles).  Pass null to switch off.
+extern "C" void mgld_conv_gemm_set_debug_counters(void* dev_ptr) { g_dbg = reinterpret_cast<long long*>(dev_ptr); }

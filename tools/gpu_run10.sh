@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out
+L=gpurun_out/run10.log; : > $L
+echo "=== pytest ops (pair auto)" >> $L
+timeout 900 python -m pytest tests/test_ops_gpu.py -q -m gpu --timeout=300 -x >> $L 2>&1
+echo "exit=$?" >> $L
+echo "=== perf conv (pair auto)" >> $L
+timeout 300 python tools/dev_perf_conv_gemm.py >> $L 2>&1
+echo "=== perf conv (pair off)" >> $L
+MGLD_CONV_PAIR=0 timeout 300 python tools/dev_perf_conv_gemm.py >> $L 2>&1
+echo "=== perf unet" >> $L
+timeout 600 python tools/dev_perf_e2e.py unet >> $L 2>&1
+echo "=== perf vae" >> $L
+timeout 600 python tools/dev_perf_e2e.py vae >> $L 2>&1
+grep -E "passed|failed|exit=|eager|graph:|VAE|TFLOP|split=|===|rror" $L | cut -c1-200 | tail -90
