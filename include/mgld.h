@@ -94,7 +94,7 @@ typedef struct mgld_conv_gemm_desc {
 int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream);
 /* bytes of workspace with which mgld_conv_gemm would use split-K for this problem (0 = it would not)                   */
 long long mgld_conv_gemm_workspace_bytes(const mgld_conv_gemm_desc* d);
-/* Development hook: per-CTA cycle counters ([grid][8] int64, device memory) filled by the following conv_gemm launches;
+/* Development hook: per-CTA cycle counters ([grid][16] int64, device memory) filled by the following conv_gemm launches;
    null switches it off (the default). */
 void mgld_conv_gemm_set_debug_counters(void* dev_ptr);
 

@@ -83,7 +83,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- TMA producer ----------------
       mbar_expect_tx(smem_u32(&q_full), kQBytes);
 #pragma unroll
@@ -104,7 +104,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- MMA issuer ----------------
       const uint32_t idesc_s = umma_idesc_f16(kQTile, kKVTile, 0, 0);  // S[128 x 128] = Q (K-major) * K^T (K-major)
       const uint32_t idesc_o = umma_idesc_f16(kQTile, DH, 0, 1);       // O[128 x DH] += P (K-major) * V (MN-major)
@@ -336,7 +336,7 @@ attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(smem_u32(&q_full), 2 * kTileBytes);
       tma_load_3d(sQ, &tmQ, smem_u32(&q_full), p.q_col0 + head * p.q_hstride, q0, b);
       tma_load_3d(sQ + kTileBytes, &tmQ, smem_u32(&q_full), p.q_col0 + head * p.q_hstride, q0 + 128, b);
@@ -350,7 +350,7 @@ attention_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc_s = umma_idesc_f16(128, kKVTile, 0, 0);
       const uint32_t idesc_o = umma_idesc_f16(128, DH, 0, 1);  // B = V, MN-major
       auto issue_s = [&](int i, int j) {

@@ -8,11 +8,15 @@
 // geometry is used by the epilogue's TMA loads (residual / SPADE input) and TMA stores, which also clip partial tiles.
 //
 // Each CTA (one per SM) loops over tiles.  Warp roles:
-//   warp 0     TMA producer: A/B ring (3-6 stages) + the residual tile of the current output tile
-//   warp 1     tcgen05.mma issuer; the fp32 accumulator is double-buffered in TMEM (2 x BLOCK_N columns), so the
-//              mainloop of tile i+1 overlaps the epilogue of tile i
-//   warps 2-5  epilogue: thread == accumulator row.  tcgen05.ld 32 columns at a time -> (+bias, activation, residual /
-//              GEGLU / SPADE math in fp32) -> fp16 -> 128B-swizzled staging tile in smem -> one TMA store per 64 columns
+//   warp 0      TMA producer of A (one elected thread): A ring (3-8 stages) + the residual tile of the current output tile
+//   warp 1      tcgen05.mma issuer; the fp32 accumulator is double-buffered in TMEM (2 x BLOCK_N columns), so the
+//               mainloop of tile i+1 overlaps the epilogue of tile i
+//   warps 6-7   TMA producers of the weight tile (half of BLOCK_N rows each)
+//   warps 2-5, 8-11  two epilogue warpgroups, thread == accumulator row, alternating over the 64-column staging panels:
+//               tcgen05.ld 32 columns -> (+bias, activation, residual / GEGLU / SPADE math in fp32) -> fp16 ->
+//               128B-swizzled staging panel in smem -> TMA store of the panel while the next one is converted
+// CTA-pair mode (clusters of 2, tcgen05 cta_group::2): the two CTAs compute M tiles 2j, 2j+1 of one N tile with one
+// M=256 MMA stream issued by the leader; each CTA stages its own A rows and only half of the weight tile.
 //
 // Replaces (reference file:line): F.conv2d in ResBlockDual openaimodel.py:401-445, SPADE spade.py:83-88,
 // VAE ResnetBlock model.py:134-161; nn.Linear in attention.py:48-75,510-524; Conv3d(3,1,1) util.py:291-310.
@@ -29,7 +33,7 @@ constexpr int kKChunk = 64;  // fp16 elements per K step = one 128-byte swizzle 
 constexpr int kABytes = kBlockM * kKChunk * 2;
 constexpr int kPanelBytes = kBlockM * 128;  // one staging panel: 128 rows x 128 bytes (64 fp16 or 32 fp32 columns)
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 256;   // warp 0: A producer, 1: MMA, 2-5: epilogue, 6-7: B producers
+constexpr int kThreads = 384;   // warp 0: A producer, 1: MMA, 2-5: epilogue group 0, 6-7: B producers, 8-11: epilogue group 1
 
 struct ConvGemmParams {
   int T, H, W;
@@ -49,10 +53,8 @@ struct ConvGemmParams {
   const float* gn_weight;
   const float* gn_bias;
   int groups, ch_per_group;
-  double* stats_out;      // optional fused GroupNorm statistics of the OUTPUT: [T, stat_groups, 2] (sum, sumsq), accumulated
-  int stat_groups, stat_cpg;
-  uint32_t off_staging, off_hstage, off_bias, off_stats;  // byte offsets from the 1024-aligned smem base
-  long long* dbg;  // optional per-CTA cycle counters [grid][8] (mgld_conv_gemm_set_debug_counters); null in production
+  uint32_t off_staging, off_hstage, off_bias;  // byte offsets from the 1024-aligned smem base
+  long long* dbg;  // optional per-CTA cycle counters [grid][16] (mgld_conv_gemm_set_debug_counters); null in production
 };
 
 __device__ __forceinline__ void act_inplace32(float* v, int act) {
@@ -127,46 +129,6 @@ __device__ __forceinline__ void store_stage32_f32(uint8_t* staging, int row, int
 }
 
 
-// Fused GroupNorm statistics of the output tile (consumer's grouping: stat_cpg channels per group).  Thread == row walks
-// its columns in increasing order, so it carries one (sum, sumsq) pair and flushes it at group boundaries: warp shuffle
-// reduction over the 32 rows of the warp (all in the same frame: BW*BH is a multiple of 32) -> shared table -> one
-// double atomicAdd per (frame, group) per tile.  Values are the fp16-rounded outputs, i.e. what the consumer will read.
-constexpr int kStatFrames = 4, kStatGroups = 72;
-struct StatAcc {
-  float s, q;
-  int g, next;
-  float* table;   // [kStatFrames][kStatGroups][2] in shared memory
-  int tf, g0, cpg, lane;
-  bool valid;
-  __device__ __forceinline__ void begin(int col, int cpg_, int g0_, int tf_, float* tab, bool valid_, int lane_) {
-    cpg = cpg_; g0 = g0_; tf = tf_; table = tab; valid = valid_; lane = lane_;
-    g = col / cpg; next = (g + 1) * cpg; s = 0.f; q = 0.f;
-  }
-  __device__ __forceinline__ void flush() {
-    float a = s, b = q;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-    if (lane == 0) {
-      float* t = table + (tf * kStatGroups + (g - g0)) * 2;
-      atomicAdd(t, a);
-      atomicAdd(t + 1, b);
-    }
-    s = 0.f; q = 0.f;
-  }
-  // v: 32 final fp32 values of columns [col, col+32); ncols = number of real output columns among them
-  __device__ __forceinline__ void add32(const float* v, int col, int ncols) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (i < ncols) {
-        if (col + i == next) { flush(); ++g; next += cpg; }
-        const float r = valid ? __half2float(__float2half_rn(v[i])) : 0.f;
-        s += r;
-        q = fmaf(r, r, q);
-      }
-    }
-  }
-};
-
 // kPair instantiation must be launched as clusters of 2 (a kernel containing cta_group::2 instructions cannot be launched
 // without a cluster: cudaErrorInvalidClusterSize), hence two instantiations rather than a runtime flag.
 template <bool kPair>
@@ -181,6 +143,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], res_full, staging_free;
   __shared__ uint32_t tmem_base_slot;
 
+  const long long dbg_k0 = clock64();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -210,10 +173,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&acc_full[b]), 1);
-      mbar_init(smem_u32(&acc_empty[b]), 128 * cs);
+      mbar_init(smem_u32(&acc_empty[b]), 256 * cs);
     }
     mbar_init(smem_u32(&res_full), 1);
-    mbar_init(smem_u32(&staging_free), 1);
+    mbar_init(smem_u32(&staging_free), 2);   // both epilogue group leaders
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -225,6 +188,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  if (p.dbg && threadIdx.x == 0) { p.dbg[blockIdx.x * 16 + 12] = clock64() - dbg_k0; }
 
   // tile -> coordinates; consecutive tiles share the weight tile (n) and walk the pixel boxes (L2-friendly)
   // returns false for the padding M tile of an odd tile count (pair mode): its box lies beyond T, loads are zero-filled
@@ -303,7 +267,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (pair_spade) tma_load_4d(smem_base + p.off_hstage, &tmH, rb, c0, x0, y0, t0);
         }
       }
-      if (p.dbg) { p.dbg[blockIdx.x * 8 + 0] = dbg_wait; p.dbg[blockIdx.x * 8 + 1] = clock64() - dbg_t0; }
+      if (p.dbg) { p.dbg[blockIdx.x * 16 + 0] = dbg_wait; p.dbg[blockIdx.x * 16 + 1] = clock64() - dbg_t0; }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
@@ -355,9 +319,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if constexpr (pair) umma_commit_pair(smem_u32(&acc_full[buf]), 3);
         else umma_commit(smem_u32(&acc_full[buf]));
       }
-      if (p.dbg) { p.dbg[blockIdx.x * 8 + 2] = dbg_wf; p.dbg[blockIdx.x * 8 + 3] = dbg_wa; p.dbg[blockIdx.x * 8 + 4] = clock64() - dbg_t0; }
+      if (p.dbg) { p.dbg[blockIdx.x * 16 + 2] = dbg_wf; p.dbg[blockIdx.x * 16 + 3] = dbg_wa; p.dbg[blockIdx.x * 16 + 4] = clock64() - dbg_t0; }
     }
-  } else if (warp >= 6) {
+  } else if (warp == 6 || warp == 7) {
     // ============================ B (weight) producers ============================
     // The tensor map's box is block_n/2 rows.  Single CTA: warps 6 and 7 each load one half (a TMA-issuing thread manages
     // one op per ~270 cycles, tools/microbench/tma_fill4.cu).  CTA pair: warp 6 loads this CTA's half, warp 7 idles.
@@ -374,160 +338,199 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int stages = p.stages;
       const uint32_t dst0 = smem_base + kABytes + slot * hbytes;
       uint32_t dst = dst0;
+      long long dbg_wb = 0;
+      const long long dbg_t0b = p.dbg ? clock64() : 0;
       for (int tile = worker; tile < total_units; tile += nworkers) {
         int x0, y0, t0, nt;
         tile_coords(tile, x0, y0, t0, nt);
         const int n0 = nt * p.block_n + half * hrows;
         const int kb = (tile % p.split_k) * p.k_per_split, ke = min(kb + p.k_per_split, num_k);
         for (int k = kb; k < ke; ++k) {
-          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          if (p.dbg) {
+            const long long tw = clock64();
+            mbar_wait(empty0 + 8 * s, ph ^ 1);
+            dbg_wb += clock64() - tw;
+          } else {
+            mbar_wait(empty0 + 8 * s, ph ^ 1);
+          }
           if constexpr (pair) tma_load_2d_pair(dst, &tmB, full0_lead + 8 * s, k * kKChunk, n0);
           else tma_load_2d(dst, &tmB, full0 + 8 * s, k * kKChunk, n0);
           dst += stage_bytes;
           if (++s == stages) { s = 0; ph ^= 1; dst = dst0; }
         }
       }
+      if (p.dbg && warp == 6) { p.dbg[blockIdx.x * 16 + 8] = dbg_wb; p.dbg[blockIdx.x * 16 + 9] = clock64() - dbg_t0b; }
     }
   } else {
-    // ============================ epilogue (warps 2..5) ============================
+    // ============================ epilogue (warps 2..5 = group 0, warps 8..11 = group 1) ============================
+    // One epilogue warp per SM sub-partition is a pure latency chain (tcgen05.ld -> math -> st.shared, IPC ~0.4), so two
+    // warpgroups share a tile: group g converts every second staging panel (64 output columns; 32 for fp32 / odd tiles).
+    // As soon as a panel is complete in shared memory its group leader issues the TMA store, which then drains while the
+    // next panel is being converted; only the last store's drain is exposed at the end of the tile.
     const int q = warp & 3;         // TMEM lane quadrant of this warp
     const int row = q * 32 + lane;  // accumulator row == tile row
-    const int e = threadIdx.x - 64;
+    const int grp = warp >= 8 ? 1 : 0;
+    const int e = grp * 128 + row;  // 0..255
+    const bool leader = row == 0;   // one per group: issues that group's TMA stores
     uint8_t* staging = smem_gen + p.off_staging;
     uint8_t* hstage = smem_gen + p.off_hstage;
     float* bias_s = reinterpret_cast<float*>(smem_gen + p.off_bias);
-    float* stat_s = reinterpret_cast<float*>(smem_gen + p.off_stats);
+    constexpr int ngroups = 2;
+    const int cols_per_panel = p.out_f32 ? 32 : p.panel_cols;
+    const int pbytes = (!p.out_f32 && p.panel_cols == 32) ? kPanelBytes / 2 : kPanelBytes;
     int lt = 0;
-    long long dbg_we = 0;
+    long long dbg_we = 0, dbg_ec = 0, dbg_es = 0;
     const long long dbg_t0e = p.dbg ? clock64() : 0;
     for (int tile = worker; tile < total_units; tile += nworkers, ++lt) {
       int x0, y0, t0, nt;
       const bool tile_valid = tile_coords(tile, x0, y0, t0, nt);
       const int buf = lt & 1;
       const int n0 = nt * p.block_n;
+      const int out_c0 = nt * p.n_out_tile;
+      const int t_store = t0 + (tile % p.split_k) * p.slab_frames;
       // bias tile -> smem (all threads passed the previous tile's closing barrier, so bias_s is free)
-      for (int i = e; i < p.block_n; i += 128)
+      for (int i = e; i < p.block_n; i += 256)
         bias_s[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
-      StatAcc sa;
-      if (p.stats_out) {
-        for (int i = e; i < kStatFrames * kStatGroups * 2; i += 128) stat_s[i] = 0.f;
-        const int r_t = row / (p.BW * p.BH), r_y = (row / p.BW) % p.BH, r_x = row % p.BW;
-        const bool valid = (x0 + r_x < p.W) && (y0 + r_y < p.H) && (t0 + r_t < p.T);
-        sa.begin(nt * p.n_out_tile, p.stat_cpg, (nt * p.n_out_tile) / p.stat_cpg, (q * 32) / (p.BW * p.BH), stat_s, valid, lane);
-      }
       const long long twe = (p.dbg && e == 0) ? clock64() : 0;
       mbar_wait(smem_u32(&acc_full[buf]), (lt >> 1) & 1);
       if (p.dbg && e == 0) dbg_we += clock64() - twe;
       tc_fence_after();
       if (p.has_res || pair_spade) mbar_wait(smem_u32(&res_full), lt & 1);
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
+      const long long tc0 = (p.dbg && e == 0) ? clock64() : 0;
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * p.acc_stride;
+      // panel `pn` of this group is complete in smem -> its leader stores it
+      auto store_panel = [&](int pn) {
+        fence_proxy_async_smem();
+        named_bar_sync(2 + grp, 128);
+        if (leader && tile_valid && out_c0 + pn * cols_per_panel < p.n_out_total) {
+          tma_store_4d(&tmOut, smem_base + p.off_staging + pn * pbytes, out_c0 + pn * cols_per_panel, x0, y0, t_store);
+          tma_store_commit();
+        }
+      };
 
       if (p.epilogue == MGLD_EPI_LINEAR) {
-        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-          float v[32];
-          tmem_ld_x32(trow + c0, reinterpret_cast<uint32_t*>(v));
-          tmem_ld_wait();
+        // Flat list of this group's 32-column steps, software-pipelined over two register buffers: the tcgen05.ld of
+        // step i+1 is in flight while step i is converted (TMEM loads are slow while the MMA is accumulating).
+        const int steps = cols_per_panel / 32;   // 32-column steps per panel (1 or 2)
+        const int my_panels = (grp < ngroups && grp < p.n_panels) ? (p.n_panels - grp + ngroups - 1) / ngroups : 0;
+        const int nsteps = my_panels * steps;
+        auto col_of = [&](int i) {
+          const int pi = steps == 2 ? (i >> 1) : i, st = steps == 2 ? (i & 1) : 0;
+          return (grp + pi * ngroups) * cols_per_panel + st * 32;
+        };
+        auto process = [&](float* v, int i) {
+          const int c0 = col_of(i);
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(bias_s + c0 + i);
-            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+          for (int u = 0; u < 32; u += 4) {
+            const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + u);
+            v[u] += bb.x; v[u + 1] += bb.y; v[u + 2] += bb.z; v[u + 3] += bb.w;
           }
           act_inplace32(v, p.act);
           if (p.has_res) {
             float r[32];
             load_stage32(staging, row, c0, r, p.panel_cols);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaf(p.alpha, v[i], p.beta * r[i]);
+            for (int u = 0; u < 32; ++u) v[u] = fmaf(p.alpha, v[u], p.beta * r[u]);
           } else if (p.alpha != 1.f) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+            for (int u = 0; u < 32; ++u) v[u] *= p.alpha;
           }
-          if (p.stats_out) sa.add32(v, nt * p.n_out_tile + c0, min(32, p.n_out_total - (nt * p.n_out_tile + c0)));
           if (p.out_f32) store_stage32_f32(staging, row, c0, v);
           else store_stage32(staging, row, c0, v, p.panel_cols);
-        }
-      } else if (p.epilogue == MGLD_EPI_GEGLU) {
-        for (int c0 = 0; c0 < 64; c0 += 32) {
-          float v[32], g[32];
-          tmem_ld_x32(trow + c0, reinterpret_cast<uint32_t*>(v));
-          tmem_ld_x32(trow + 64 + c0, reinterpret_cast<uint32_t*>(g));
+          if (steps == 1 || (i & 1)) {   // panel complete
+            if (i == nsteps - 1) {       // ... and it was the last: this thread's accumulator rows are drained
+              tc_fence_before();
+              if (!pair || rank == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+              else mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[buf]), 0));   // the pair's MMA issuer lives in the leader
+            }
+            store_panel(c0 / cols_per_panel);
+          }
+        };
+        float va[32], vb[32];
+        if (nsteps > 0) tmem_ld_x32(trow + col_of(0), reinterpret_cast<uint32_t*>(va));
+        for (int i = 0; i < nsteps; i += 2) {
           tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) { v[i] += bias_s[c0 + i]; g[i] += bias_s[64 + c0 + i]; }
-          act_inplace32(g, MGLD_ACT_GELU);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= g[i];
-          if (p.has_res) {
-            float r[32];
-            load_stage32(staging, row, c0, r, p.panel_cols);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaf(p.alpha, v[i], p.beta * r[i]);
+          if (i + 1 < nsteps) tmem_ld_x32(trow + col_of(i + 1), reinterpret_cast<uint32_t*>(vb));
+          process(va, i);
+          if (i + 1 < nsteps) {
+            tmem_ld_wait();
+            if (i + 2 < nsteps) tmem_ld_x32(trow + col_of(i + 2), reinterpret_cast<uint32_t*>(va));
+            process(vb, i + 1);
           }
-          if (p.stats_out) sa.add32(v, nt * 64 + c0, 32);
-          store_stage32(staging, row, c0, v, 64);
         }
-      } else {  // SPADE: out = beta*res + GNaffine(h) * (1 + gamma) + beta_s
-        const int tt = min(t0 + row / (p.BW * p.BH), p.T - 1);
-        const int cbase = nt * 64;
-        for (int c0 = 0; c0 < 64; c0 += 32) {
-          float gm[32], bt[32], hv[32];
-          tmem_ld_x32(trow + c0, reinterpret_cast<uint32_t*>(gm));
-          tmem_ld_x32(trow + 64 + c0, reinterpret_cast<uint32_t*>(bt));
-          tmem_ld_wait();
-          load_stage32(hstage, row, c0, hv, 64);
+        if (nsteps == 0) {   // a group without panels still releases the accumulator
+          tc_fence_before();
+          if (!pair || rank == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+          else mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[buf]), 0));
+        }
+      } else {
+        // pair epilogues: ONE 64-column output panel; group g converts its 32-column half
+        if (grp < ngroups) {
+          for (int c0 = grp * 32; c0 < 64; c0 += ngroups * 32) {
+            if (p.epilogue == MGLD_EPI_GEGLU) {
+              float v[32], g[32];
+              tmem_ld_x32(trow + c0, reinterpret_cast<uint32_t*>(v));
+              tmem_ld_x32(trow + 64 + c0, reinterpret_cast<uint32_t*>(g));
+              tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int c = cbase + c0 + i;
-            const int g = c / p.ch_per_group;
-            const float2 st = __ldg(reinterpret_cast<const float2*>(p.gn_stats) + tt * p.groups + g);
-            const float xn = fmaf((hv[i] - st.x) * st.y, __ldg(p.gn_weight + c), __ldg(p.gn_bias + c));
-            gm[i] = fmaf(xn, 1.f + gm[i] + bias_s[c0 + i], bt[i] + bias_s[64 + c0 + i]);
-          }
-          if (p.has_res) {
-            float r[32];
-            load_stage32(staging, row, c0, r, p.panel_cols);
+              for (int i = 0; i < 32; ++i) { v[i] += bias_s[c0 + i]; g[i] += bias_s[64 + c0 + i]; }
+              act_inplace32(g, MGLD_ACT_GELU);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) gm[i] = fmaf(p.beta, r[i], gm[i]);
+              for (int i = 0; i < 32; ++i) v[i] *= g[i];
+              if (p.has_res) {
+                float r[32];
+                load_stage32(staging, row, c0, r, p.panel_cols);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = fmaf(p.alpha, v[i], p.beta * r[i]);
+              }
+              store_stage32(staging, row, c0, v, 64);
+            } else {  // SPADE: out = beta*res + GNaffine(h) * (1 + gamma) + beta_s
+              const int tt = min(t0 + row / (p.BW * p.BH), p.T - 1);
+              const int cbase = nt * 64;
+              float gm[32], bt[32], hv[32];
+              tmem_ld_x32(trow + c0, reinterpret_cast<uint32_t*>(gm));
+              tmem_ld_x32(trow + 64 + c0, reinterpret_cast<uint32_t*>(bt));
+              tmem_ld_wait();
+              load_stage32(hstage, row, c0, hv, 64);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int c = cbase + c0 + i;
+                const int g = c / p.ch_per_group;
+                const float2 st = __ldg(reinterpret_cast<const float2*>(p.gn_stats) + tt * p.groups + g);
+                const float xn = fmaf((hv[i] - st.x) * st.y, __ldg(p.gn_weight + c), __ldg(p.gn_bias + c));
+                gm[i] = fmaf(xn, 1.f + gm[i] + bias_s[c0 + i], bt[i] + bias_s[64 + c0 + i]);
+              }
+              if (p.has_res) {
+                float r[32];
+                load_stage32(staging, row, c0, r, p.panel_cols);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) gm[i] = fmaf(p.beta, r[i], gm[i]);
+              }
+              store_stage32(staging, row, c0, gm, 64);
+            }
           }
-          if (p.stats_out) sa.add32(gm, nt * 64 + c0, 32);
-          store_stage32(staging, row, c0, gm, 64);
+        }
+        tc_fence_before();
+        if (!pair || rank == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+        else mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[buf]), 0));
+        fence_proxy_async_smem();
+        named_bar_sync(1, 256);   // both halves of the panel are in smem
+        if (e == 0 && tile_valid) {
+          tma_store_4d(&tmOut, smem_base + p.off_staging, out_c0, x0, y0, t_store);
+          tma_store_commit();
         }
       }
-      // accumulator buffer drained -> the MMA warp may start tile lt+2 in it
-      tc_fence_before();
-      if (!pair || rank == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
-      else mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[buf]), 0));   // the pair's MMA issuer lives in the leader
-      if (p.stats_out) sa.flush();
-      // staging tile complete -> one thread issues the TMA stores
-      fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (p.stats_out) {
-        const int g0 = (nt * p.n_out_tile) / p.stat_cpg;
-        for (int i = e; i < kStatFrames * kStatGroups * 2; i += 128) {
-          const float val = stat_s[i];
-          const int tf = i / (kStatGroups * 2), gi = (i / 2) % kStatGroups;
-          if (val != 0.f && t0 + tf < p.T && g0 + gi < p.stat_groups)
-            atomicAdd(p.stats_out + (static_cast<long long>(t0 + tf) * p.stat_groups + g0 + gi) * 2 + (i & 1), (double)val);
-        }
-      }
-      if (e == 0) {
-        const int c0 = nt * p.n_out_tile;
-        const int cols_per_panel = p.out_f32 ? 32 : p.panel_cols;
-        const int pbytes = (!p.out_f32 && p.panel_cols == 32) ? kPanelBytes / 2 : kPanelBytes;
-        for (int pn = 0; pn < p.n_panels; ++pn) {
-          if (tile_valid && c0 + pn * cols_per_panel < p.n_out_total)
-            tma_store_4d(&tmOut, smem_base + p.off_staging + pn * pbytes, c0 + pn * cols_per_panel, x0, y0,
-                         t0 + (tile % p.split_k) * p.slab_frames);
-        }
-        tma_store_commit();
-        tma_store_wait_read();  // staging may be overwritten (by the next residual load / next tile's epilogue)
+      const long long tc1 = (p.dbg && e == 0) ? clock64() : 0;
+      if (leader) {
+        tma_store_wait_read();  // this group's stores have read their panels: staging may be overwritten
         if (p.has_res || pair_spade) mbar_arrive(smem_u32(&staging_free));
+        if (p.dbg && e == 0) { dbg_ec += tc1 - tc0; dbg_es += clock64() - tc1; }
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
     }
-    if (e == 0) tma_store_wait_all();
-    if (p.dbg && e == 0) { p.dbg[blockIdx.x * 8 + 5] = dbg_we; p.dbg[blockIdx.x * 8 + 6] = clock64() - dbg_t0e; p.dbg[blockIdx.x * 8 + 7] = lt; }
+    if (leader) tma_store_wait_all();
+    if (p.dbg && e == 0) { p.dbg[blockIdx.x * 16 + 5] = dbg_we; p.dbg[blockIdx.x * 16 + 6] = clock64() - dbg_t0e; p.dbg[blockIdx.x * 16 + 7] = lt; p.dbg[blockIdx.x * 16 + 10] = dbg_ec; p.dbg[blockIdx.x * 16 + 11] = dbg_es; }
   }
 
   tc_fence_before();
@@ -538,6 +541,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if constexpr (pair) tmem_dealloc_pair(tmem_base, p.tmem_cols);
     else tmem_dealloc(tmem_base, p.tmem_cols);
   }
+  if (p.dbg && threadIdx.x == 0) { p.dbg[blockIdx.x * 16 + 13] = clock64() - dbg_k0; }
 }
 
 
@@ -734,8 +738,8 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
   const int sms = num_sms();
   {
     const int pm = pair_mode_env();
-    // a pair needs two M tiles; fused statistics keep the single-CTA path
-    p.cta_pair = (p.tiles_m >= 2 && !d->stats_out && pm != 0) ? 1 : 0;
+    // a pair needs two M tiles
+    p.cta_pair = (p.tiles_m >= 2 && pm != 0) ? 1 : 0;
   }
   const int workers = p.cta_pair ? sms / 2 : sms;
   const int tiles_mw = p.cta_pair ? ceil_div(p.tiles_m, 2) : p.tiles_m;
@@ -758,21 +762,13 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
   p.has_res = d->res != nullptr; p.out_f32 = d->out_f32;
   p.gn_stats = d->gn_stats; p.gn_weight = d->gn_weight; p.gn_bias = d->gn_bias;
   p.groups = d->groups; p.ch_per_group = d->groups > 0 ? p.n_out_total / d->groups : 1;
-  p.stats_out = d->stats_out; p.stat_groups = d->stats_groups;
   p.dbg = g_dbg;
-  p.stat_cpg = d->stats_groups > 0 ? p.n_out_total / d->stats_groups : 1;
-  if (d->stats_out) {
-    MGLD_CHECK_ARG(d->stats_groups > 0 && p.n_out_total % d->stats_groups == 0 && !d->out_f32,
-                   "conv_gemm: stats_groups=%d must divide the %d output channels (fp16 out)", d->stats_groups, p.n_out_total);
-    MGLD_CHECK_ARG((p.BW * p.BH) % 32 == 0 && p.BT <= kStatFrames && p.n_out_tile / p.stat_cpg + 2 <= kStatGroups,
-                   "conv_gemm: fused statistics need >= 32 pixels per frame in a tile (box %dx%dx%d)", p.BW, p.BH, p.BT);
-  }
 
   // shared memory plan: [A/B ring][staging panels][h panel (SPADE)][bias]
   const int stage_bytes = kABytes + (p.block_n / (p.cta_pair ? 2 : 1)) * 128;
   const int staging_bytes = d->out_f32 ? p.n_panels * kPanelBytes : p.n_out_tile * kBlockM * 2;
   const int hstage_bytes = d->epilogue == MGLD_EPI_SPADE ? kPanelBytes : 0;
-  const int fixed = staging_bytes + hstage_bytes + 1024 /*bias*/ + kStatFrames * kStatGroups * 8 /*stats*/ + 1024 /*alignment slack*/;
+  const int fixed = staging_bytes + hstage_bytes + 1024 /*bias*/ + 1024 /*alignment slack*/;
   int stages = (224 * 1024 - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   MGLD_CHECK_ARG(stages >= 2, "conv_gemm: tile does not fit in shared memory (block_n=%d)", p.block_n);
@@ -780,8 +776,7 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
   p.off_staging = stages * stage_bytes;
   p.off_hstage = p.off_staging + staging_bytes;
   p.off_bias = p.off_hstage + hstage_bytes;
-  p.off_stats = p.off_bias + 1024;
-  const int smem = p.off_stats + kStatFrames * kStatGroups * 2 * 4 + 1024;
+  const int smem = p.off_bias + 1024 + 1024;
 
   // tensor maps
   const int lda = d->lda > 0 ? d->lda : d->C1;
@@ -856,7 +851,7 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
 
 // ---- split-K path: pass 1 = raw fp32 partial tiles into workspace slabs, pass 2 = deterministic sum + epilogue ---------
 static bool split_plan(const mgld_conv_gemm_desc* d, int* S, int* bn, size_t* bytes, int* ldws, int* slab_frames) {
-  if (d->out_f32 || d->stats_out) return false;
+  if (d->out_f32) return false;
   const bool pair = d->epilogue == MGLD_EPI_GEGLU || d->epilogue == MGLD_EPI_SPADE;
   int BW, BH, BT;
   pick_box(d->T, d->H, d->W, &BW, &BH, &BT);
@@ -882,9 +877,23 @@ extern "C" long long mgld_conv_gemm_workspace_bytes(const mgld_conv_gemm_desc* d
   return (long long)bytes;
 }
 
+static int conv_gemm_dispatch(const mgld_conv_gemm_desc* d, void* stream_);
+
 extern "C" int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream_) {
   if (!initialised()) { set_error("mgld_init() has not been called"); return MGLD_ERR_NOT_INIT; }
   MGLD_CHECK_ARG(d && d->a && d->w && d->out, "conv_gemm: null pointer");
+  int rc = conv_gemm_dispatch(d, stream_);
+  if (rc || !d->stats_out) return rc;
+  // GroupNorm statistics of the output for its consumer: a streaming pass over the (L2-resident) output.  Accumulating them
+  // in the conv epilogue (shuffles + shared/global atomics per tile) was measured slower than this pass (profiles/
+  // r01_dev_run7_fused_stats_regression.log), so the epilogue stays lean.
+  MGLD_CHECK_ARG(!d->out_f32 && d->stats_groups > 0, "conv_gemm: stats_out needs fp16 output and stats_groups > 0");
+  const int n_out = d->epilogue == MGLD_EPI_LINEAR ? d->N : d->N / 2;
+  return mgld_gn_stats_f16(reinterpret_cast<const __half*>(d->out) + d->out_col0, n_out, d->ldout, nullptr, 0, 0, d->T,
+                           d->H * d->W, d->stats_groups, d->stats_out, stream_);
+}
+
+static int conv_gemm_dispatch(const mgld_conv_gemm_desc* d, void* stream_) {
   int S, bn, ldws, sf;
   size_t bytes;
   if (!d->workspace || !split_plan(d, &S, &bn, &bytes, &ldws, &sf) || (size_t)d->workspace_bytes < bytes)
@@ -915,7 +924,7 @@ extern "C" int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream_) {
   return MGLD_OK;
 }
 
-// Development hook: per-CTA cycle counters of the next conv_gemm launches ([grid][8] int64 in device memory: A-producer
+// Development hook: per-CTA cycle counters of the next conv_gemm launches ([grid][16] int64 in device memory: A-producer
 // wait-on-empty, A-producer total, MMA wait-on-full, MMA wait-on-accumulator, MMA total, epilogue wait, epilogue total,
-// tiles).  Pass null to switch off.
+// tiles, B-producer wait-on-empty, B-producer total).  Pass null to switch off.
 extern "C" void mgld_conv_gemm_set_debug_counters(void* dev_ptr) { g_dbg = reinterpret_cast<long long*>(dev_ptr); }
