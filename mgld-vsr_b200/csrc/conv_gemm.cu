@@ -131,7 +131,11 @@ __device__ __forceinline__ void store_stage32_f32(uint8_t* staging, int row, int
 
 // kPair instantiation must be launched as clusters of 2 (a kernel containing cta_group::2 instructions cannot be launched
 // without a cluster: cudaErrorInvalidClusterSize), hence two instantiations rather than a runtime flag.
-template <bool kPair>
+// kVariant: 0 = every epilogue option is a runtime flag; 1..4 = the common LINEAR epilogues with the flags folded at
+// compile time (1: +bias; 2: +bias, residual; 3: raw fp32 out (split-K partials); 4: +bias, SiLU).  With runtime flags the
+// per-32-column step hops through six distant code islands (parameter load -> branch), paying instruction-fetch and
+// constant-load latency on every hop in a single-warp latency chain.
+template <bool kPair, int kVariant>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
@@ -161,7 +165,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int stage_bytes = kABytes + b_rows * kKChunk * 2;
   const int num_k = p.taps * p.kchunks;
   const int total_units = tiles_mw * p.tiles_n * p.split_k;  // work units of a worker (CTA or CTA pair)
-  const bool pair_spade = p.epilogue == MGLD_EPI_SPADE;
+  constexpr bool kGen = kVariant == 0;
+  const int epi = kGen ? p.epilogue : MGLD_EPI_LINEAR;
+  const int act = kGen ? p.act : (kVariant == 4 ? MGLD_ACT_SILU : MGLD_ACT_NONE);
+  const bool has_res = kGen ? (p.has_res != 0) : (kVariant == 2);
+  const bool out_f32 = kGen ? (p.out_f32 != 0) : (kVariant == 3);
+  const bool unit_alpha = kGen ? (p.alpha == 1.f) : true;   // variants 1, 3, 4 require alpha == 1; 2 uses the residual form
+  const bool pair_spade = epi == MGLD_EPI_SPADE;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -254,12 +264,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           sa += stage_bytes;
           if (++s == stages) { s = 0; ph ^= 1; sa = smem_base; }
         }
-        if (p.has_res || pair_spade) {
+        if (has_res || pair_spade) {
           // residual (and SPADE's h) tile of THIS output tile, into the staging buffers the epilogue will overwrite
           mbar_wait(smem_u32(&staging_free), (lt & 1) ^ 1);
           const uint32_t rb = smem_u32(&res_full);
           const int c0 = nt * p.n_out_tile;
-          const int np = p.has_res ? p.n_panels : 0;
+          const int np = has_res ? p.n_panels : 0;
           mbar_expect_tx(rb, np * (p.panel_cols == 32 ? kPanelBytes / 2 : kPanelBytes) + (pair_spade ? kPanelBytes : 0));
           const int pbytes = p.panel_cols == 32 ? kPanelBytes / 2 : kPanelBytes;
           for (int q = 0; q < np; ++q)
@@ -374,28 +384,40 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool leader = row == 0;   // one per group: issues that group's TMA stores
     uint8_t* staging = smem_gen + p.off_staging;
     uint8_t* hstage = smem_gen + p.off_hstage;
-    float* bias_s = reinterpret_cast<float*>(smem_gen + p.off_bias);
+    float* bias_s0 = reinterpret_cast<float*>(smem_gen + p.off_bias);   // two buffers of 256 floats (tile parity)
     constexpr int ngroups = 2;
-    const int cols_per_panel = p.out_f32 ? 32 : p.panel_cols;
-    const int pbytes = (!p.out_f32 && p.panel_cols == 32) ? kPanelBytes / 2 : kPanelBytes;
+    const int cols_per_panel = out_f32 ? 32 : p.panel_cols;
+    const int pbytes = (!out_f32 && p.panel_cols == 32) ? kPanelBytes / 2 : kPanelBytes;
     int lt = 0;
     long long dbg_we = 0, dbg_ec = 0, dbg_es = 0;
     const long long dbg_t0e = p.dbg ? clock64() : 0;
+    // Without a residual tile nobody else touches the staging panels, so the drain of a tile's TMA stores is only awaited
+    // at the start of the NEXT tile's conversion (it has long finished by then) and the closing barrier disappears.
+    const bool defer_drain = !(has_res || pair_spade);
+    auto bias_of = [&](int unit) {   // this thread's bias element of work unit `unit` (block_n <= 256 = one per thread)
+      const int n = ((unit / p.split_k) / tiles_mw) * p.block_n + e;
+      return (p.bias && e < p.block_n && n < p.N) ? __ldg(p.bias + n) : 0.f;
+    };
+    if (worker < total_units) bias_s0[e] = bias_of(worker);
     for (int tile = worker; tile < total_units; tile += nworkers, ++lt) {
       int x0, y0, t0, nt;
       const bool tile_valid = tile_coords(tile, x0, y0, t0, nt);
       const int buf = lt & 1;
-      const int n0 = nt * p.block_n;
       const int out_c0 = nt * p.n_out_tile;
       const int t_store = t0 + (tile % p.split_k) * p.slab_frames;
-      // bias tile -> smem (all threads passed the previous tile's closing barrier, so bias_s is free)
-      for (int i = e; i < p.block_n; i += 256)
-        bias_s[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+      const float* bias_s = bias_s0 + (lt & 1) * 256;
+      // the next tile's bias element travels in a register during this tile's conversion (global-load latency hidden)
+      const float bias_next = (tile + nworkers < total_units) ? bias_of(tile + nworkers) : 0.f;
       const long long twe = (p.dbg && e == 0) ? clock64() : 0;
       mbar_wait(smem_u32(&acc_full[buf]), (lt >> 1) & 1);
       if (p.dbg && e == 0) dbg_we += clock64() - twe;
       tc_fence_after();
-      if (p.has_res || pair_spade) mbar_wait(smem_u32(&res_full), lt & 1);
+      if (has_res || pair_spade) mbar_wait(smem_u32(&res_full), lt & 1);
+      if (defer_drain && leader) {
+        const long long td = (p.dbg && e == 0) ? clock64() : 0;
+        tma_store_wait_read();   // the previous tile's stores of this group have read their panels
+        if (p.dbg && e == 0) dbg_es += clock64() - td;
+      }
       named_bar_sync(1, 256);
       const long long tc0 = (p.dbg && e == 0) ? clock64() : 0;
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * p.acc_stride;
@@ -409,7 +431,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       };
 
-      if (p.epilogue == MGLD_EPI_LINEAR) {
+      if (epi == MGLD_EPI_LINEAR) {
         // Flat list of this group's 32-column steps, software-pipelined over two register buffers: the tcgen05.ld of
         // step i+1 is in flight while step i is converted (TMEM loads are slow while the MMA is accumulating).
         const int steps = cols_per_panel / 32;   // 32-column steps per panel (1 or 2)
@@ -426,17 +448,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + u);
             v[u] += bb.x; v[u + 1] += bb.y; v[u + 2] += bb.z; v[u + 3] += bb.w;
           }
-          act_inplace32(v, p.act);
-          if (p.has_res) {
+          act_inplace32(v, act);
+          if (has_res) {
             float r[32];
             load_stage32(staging, row, c0, r, p.panel_cols);
 #pragma unroll
             for (int u = 0; u < 32; ++u) v[u] = fmaf(p.alpha, v[u], p.beta * r[u]);
-          } else if (p.alpha != 1.f) {
+          } else if (!unit_alpha) {
 #pragma unroll
             for (int u = 0; u < 32; ++u) v[u] *= p.alpha;
           }
-          if (p.out_f32) store_stage32_f32(staging, row, c0, v);
+          if (out_f32) store_stage32_f32(staging, row, c0, v);
           else store_stage32(staging, row, c0, v, p.panel_cols);
           if (steps == 1 || (i & 1)) {   // panel complete
             if (i == nsteps - 1) {       // ... and it was the last: this thread's accumulator rows are drained
@@ -468,7 +490,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // pair epilogues: ONE 64-column output panel; group g converts its 32-column half
         if (grp < ngroups) {
           for (int c0 = grp * 32; c0 < 64; c0 += ngroups * 32) {
-            if (p.epilogue == MGLD_EPI_GEGLU) {
+            if (epi == MGLD_EPI_GEGLU) {
               float v[32], g[32];
               tmem_ld_x32(trow + c0, reinterpret_cast<uint32_t*>(v));
               tmem_ld_x32(trow + 64 + c0, reinterpret_cast<uint32_t*>(g));
@@ -478,7 +500,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               act_inplace32(g, MGLD_ACT_GELU);
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] *= g[i];
-              if (p.has_res) {
+              if (has_res) {
                 float r[32];
                 load_stage32(staging, row, c0, r, p.panel_cols);
 #pragma unroll
@@ -501,7 +523,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const float xn = fmaf((hv[i] - st.x) * st.y, __ldg(p.gn_weight + c), __ldg(p.gn_bias + c));
                 gm[i] = fmaf(xn, 1.f + gm[i] + bias_s[c0 + i], bt[i] + bias_s[64 + c0 + i]);
               }
-              if (p.has_res) {
+              if (has_res) {
                 float r[32];
                 load_stage32(staging, row, c0, r, p.panel_cols);
 #pragma unroll
@@ -522,12 +544,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       const long long tc1 = (p.dbg && e == 0) ? clock64() : 0;
-      if (leader) {
-        tma_store_wait_read();  // this group's stores have read their panels: staging may be overwritten
-        if (p.has_res || pair_spade) mbar_arrive(smem_u32(&staging_free));
-        if (p.dbg && e == 0) { dbg_ec += tc1 - tc0; dbg_es += clock64() - tc1; }
+      bias_s0[((lt + 1) & 1) * 256 + e] = bias_next;   // read after the next tile's opening barrier
+      if (p.dbg && e == 0) dbg_ec += tc1 - tc0;
+      if (!defer_drain) {
+        if (leader) {
+          tma_store_wait_read();  // this group's stores have read their panels: the residual of the next tile may land
+          mbar_arrive(smem_u32(&staging_free));
+          if (p.dbg && e == 0) dbg_es += clock64() - tc1;
+        }
+        named_bar_sync(1, 256);
       }
-      named_bar_sync(1, 256);
     }
     if (leader) tma_store_wait_all();
     if (p.dbg && e == 0) { p.dbg[blockIdx.x * 16 + 5] = dbg_we; p.dbg[blockIdx.x * 16 + 6] = clock64() - dbg_t0e; p.dbg[blockIdx.x * 16 + 7] = lt; p.dbg[blockIdx.x * 16 + 10] = dbg_ec; p.dbg[blockIdx.x * 16 + 11] = dbg_es; }
@@ -738,8 +764,10 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
   const int sms = num_sms();
   {
     const int pm = pair_mode_env();
-    // a pair needs two M tiles
-    p.cta_pair = (p.tiles_m >= 2 && pm != 0) ? 1 : 0;
+    // a pair needs two M tiles.  Measured (profiles/r01_dev_run12*.log): pairs win on long-K convolutions with many M
+    // tiles (VAE 256^2/512^2: +4..10%) and lose on short-K GEMMs and few-tile layers, so auto mode is conservative.
+    const bool big = p.tiles_m >= 512 && ntaps * p.kchunks >= 18;
+    p.cta_pair = (p.tiles_m >= 2 && (pm == 1 || (pm < 0 && big))) ? 1 : 0;
   }
   const int workers = p.cta_pair ? sms / 2 : sms;
   const int tiles_mw = p.cta_pair ? ceil_div(p.tiles_m, 2) : p.tiles_m;
@@ -768,7 +796,7 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
   const int stage_bytes = kABytes + (p.block_n / (p.cta_pair ? 2 : 1)) * 128;
   const int staging_bytes = d->out_f32 ? p.n_panels * kPanelBytes : p.n_out_tile * kBlockM * 2;
   const int hstage_bytes = d->epilogue == MGLD_EPI_SPADE ? kPanelBytes : 0;
-  const int fixed = staging_bytes + hstage_bytes + 1024 /*bias*/ + 1024 /*alignment slack*/;
+  const int fixed = staging_bytes + hstage_bytes + 2048 /*bias, two tiles*/ + 1024 /*alignment slack*/;
   int stages = (224 * 1024 - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   MGLD_CHECK_ARG(stages >= 2, "conv_gemm: tile does not fit in shared memory (block_n=%d)", p.block_n);
@@ -776,7 +804,7 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
   p.off_staging = stages * stage_bytes;
   p.off_hstage = p.off_staging + staging_bytes;
   p.off_bias = p.off_hstage + hstage_bytes;
-  const int smem = p.off_bias + 1024 + 1024;
+  const int smem = p.off_bias + 2048 + 1024;
 
   // tensor maps
   const int lda = d->lda > 0 ? d->lda : d->C1;
@@ -815,15 +843,33 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
     else tmH = tmA;
   }
 
+  using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvGemmParams);
+  static const KernelFn kKernels[2][5] = {
+      {conv_gemm_kernel<false, 0>, conv_gemm_kernel<false, 1>, conv_gemm_kernel<false, 2>, conv_gemm_kernel<false, 3>,
+       conv_gemm_kernel<false, 4>},
+      {conv_gemm_kernel<true, 0>, conv_gemm_kernel<true, 1>, conv_gemm_kernel<true, 2>, conv_gemm_kernel<true, 3>,
+       conv_gemm_kernel<true, 4>}};
   if (!g_attr_set) {
-    MGLD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    MGLD_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < 5; ++j)
+        MGLD_CUDA(cudaFuncSetAttribute(kKernels[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     g_attr_set = true;
   }
+  // epilogue variant with compile-time flags (see the kernel's comment); MGLD_CONV_VARIANT=0 forces the generic kernel
+  int variant = 0;
+  if (d->epilogue == MGLD_EPI_LINEAR && d->act == MGLD_ACT_NONE) {
+    if (!d->res && !d->out_f32 && d->alpha == 1.f) variant = 1;
+    else if (d->res && !d->out_f32) variant = 2;
+    else if (!d->res && d->out_f32 && d->alpha == 1.f) variant = 3;
+  } else if (d->epilogue == MGLD_EPI_LINEAR && d->act == MGLD_ACT_SILU && !d->res && !d->out_f32 && d->alpha == 1.f) {
+    variant = 4;
+  }
+  { const char* ev = getenv("MGLD_CONV_VARIANT"); if (ev && atoi(ev) == 0) variant = 0; }
+  const KernelFn kernel = kKernels[p.cta_pair ? 1 : 0][variant];
   const int total_units = tiles_mw * p.tiles_n * p.split_k;
   if (!p.cta_pair) {
     dim3 grid(total_units < sms ? total_units : sms, 1, 1);
-    conv_gemm_kernel<false><<<grid, kThreads, smem, stream>>>(tmA, tmA2, tmB, tmOut, tmRes, tmH, p);
+    kernel<<<grid, kThreads, smem, stream>>>(tmA, tmA2, tmB, tmOut, tmRes, tmH, p);
   } else {
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
@@ -837,13 +883,13 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
       cfg.gridDim = dim3(2 * (sms / 2), 1, 1);
       cfg.dynamicSmemBytes = 226 * 1024;
       int n = 0;
-      MGLD_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<true>, &cfg));
+      MGLD_CUDA(cudaOccupancyMaxActiveClusters(&n, kKernels[1][0], &cfg));
       g_max_pairs = n > 0 ? (n < sms / 2 ? n : sms / 2) : 1;
       cfg.dynamicSmemBytes = smem;
     }
     const int pairs = total_units < g_max_pairs ? total_units : g_max_pairs;
     cfg.gridDim = dim3(2 * pairs, 1, 1);
-    MGLD_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, tmA, tmA2, tmB, tmOut, tmRes, tmH, p));
+    MGLD_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmA, tmA2, tmB, tmOut, tmRes, tmH, p));
   }
   MGLD_LAUNCH_CHECK("conv_gemm_kernel");
   return MGLD_OK;
