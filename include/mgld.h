@@ -164,6 +164,16 @@ int mgld_gn_finalize(const double* sums, float* stats, int T, int groups, int HW
 int mgld_gn_apply_f16(const void* x1, int C1, int ld1, const void* x2, int C2, int ld2, int T, int HW, int groups,
                       const double* sums, double eps, const float* gamma, const float* beta, int silu, void* out,
                       int ldo, void* stream);
+/* GroupNorm [+SiLU] in ONE launch where the per-CTA patch fits in registers (UNet / struct-encoder shapes): statistics and
+ * normalisation share a single read of the activation; CTAs of a frame reduce over distributed shared memory (thread-block
+ * clusters).  out (dense [T*HW, C1+C2], row pitch ldo) and stats_out ((mean, rstd) fp32 [T, groups, 2], the SPADE
+ * epilogue's operand) are each optional.  Shapes that do not fit (mgld_group_norm_fused_supported() == 0, e.g. the VAE's
+ * 256^2+ maps) run gn_stats / gn_finalize / gn_apply internally and need `scratch`: [T, groups, 2] doubles, zeroed.
+ * GroupNorm32 util.py:199-216 (eps 1e-5), Normalize model.py:80 (eps 1e-6).                                             */
+int mgld_group_norm_f16(const void* x1, int C1, int ld1, const void* x2, int C2, int ld2, int T, int HW, int groups,
+                        double eps, const float* gamma, const float* beta, int silu, void* out, int ldo,
+                        float* stats_out, double* scratch, void* stream);
+int mgld_group_norm_fused_supported(int C, int T, int HW, int groups);
 /* nn.LayerNorm over the last dim (attention.py:132,423-425)                                                          */
 int mgld_layernorm_f16(const void* x, int ldx, int M, int C, const float* gamma, const float* beta, float eps,
                        void* out, int ldo, void* stream);

@@ -192,6 +192,7 @@ class AutoencoderKL(_ModuleBase):
     def encode(self, x, return_encfea=False):
         """autoencoder.py:347-353"""
         self.pool.reset(x.shape[0], x.device)
+        self.ops.stats_pool_reset()
         moments = self.ops.conv_small_f32(self.encoder(self.ops, x, pool=self.pool), self.qw, self.qb)
         post = DiagonalGaussianDistribution(moments, self.ops)
         return (post, moments) if return_encfea else post
@@ -361,6 +362,7 @@ class VideoAutoencoderKLResi(_ModuleBase):
     def encode(self, x):
         """autoencoder.py:1674-1679 -> (posterior, enc_fea); enc_fea: NCHW-shaped fp16 (channels-last) feature taps."""
         self.pool.reset(x.shape[0], x.device)
+        self.ops.stats_pool_reset()
         h, fea = self.encoder(self.ops, x, return_fea=True, pool=self.pool)
         moments = self.ops.conv_small_f32(h, self.qw, self.qb)
         return DiagonalGaussianDistribution(moments, self.ops), [nchw_view(f) for f in fea]
@@ -368,5 +370,6 @@ class VideoAutoencoderKLResi(_ModuleBase):
     def decode(self, z, enc_fea):
         """autoencoder.py:1687-1690 -> (T,3,H,W) fp32"""
         self.pool.reset(z.shape[0], z.device)
+        self.ops.stats_pool_reset()
         z = self.ops.conv_small_f32(z.float().contiguous(), self.pqw, self.pqb)
         return self.decoder(self.ops, z, enc_fea, pool=self.pool)

@@ -7,9 +7,11 @@
 // (model.py:75-77), nn.LayerNorm (attention.py:132,423-425), the softmax inside memory_efficient_attention at
 // model.py:294.
 #include <math.h>
+#include <string.h>
 
 #include "../../include/mgld.h"
 #include "common.h"
+#include "ptx.cuh"
 
 namespace mgld {
 
@@ -160,6 +162,149 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, int ld1, 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Single-launch GroupNorm (+SiLU): statistics and normalisation in ONE pass over HBM.  A CTA owns a (rows x channels)
+// patch of one frame -- `cc` channels (whole groups, whole 16-byte vectors) of `rp` rows -- and keeps it in REGISTERS
+// (thread = fixed 8-channel column, up to kItems rows).  The `cs` CTAs that share a channel range of a frame form a
+// thread-block cluster: partial (sum, sumsq) per group go to each CTA's shared memory, every CTA sums all partials over
+// distributed shared memory in the same fixed order (so all agree bit-for-bit), then normalises its registers and stores.
+// Replaces zero-fill + gn_stats + (gn_finalize) + gn_apply: 3-4 launches and a second read of the activation.
+// ---------------------------------------------------------------------------------------------------------------------
+struct GnFusedParams {
+  const __half* x1; int C1, ld1;
+  const __half* x2; int C2, ld2;
+  int HW, G, cpg;
+  int cc, vpc, R, rp, cs;   // channels per CTA, 8-channel vectors per row of the patch, row lanes, rows per CTA, cluster size
+  double eps;
+  const float* gamma; const float* beta;
+  int silu;
+  __half* out; int ldo;     // may be null: statistics only
+  float* stats_out;         // may be null; (mean, rstd) [T, G, 2] for the SPADE epilogue of conv_gemm
+};
+constexpr int kGnFusedThreads = 512;
+constexpr int kGnFusedMaxGroups = 64;   // groups per CTA patch
+
+__device__ __forceinline__ float ld_shared_cluster_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+template <int kItems>
+__global__ void __launch_bounds__(kGnFusedThreads, 1) gn_fused_kernel(const GnFusedParams p) {
+  extern __shared__ float tab[];                  // [2][R][cc]: per-thread channel partials (sum | sumsq)
+  __shared__ float chs[2 * kGnFusedThreads];      // per-channel (sum | sumsq) of this CTA's patch
+  __shared__ float part[2 * kGnFusedMaxGroups];   // this CTA's partial (sum, sumsq) per local group
+  __shared__ float stat[2 * kGnFusedMaxGroups];   // (mean, rstd) per local group
+  const int tid = threadIdx.x;
+  const int rank = p.cs > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int t = blockIdx.z;
+  const int c_lo = blockIdx.y * p.cc;
+  const int r_lo = rank * p.rp;
+  const int rows = max(0, min(p.rp, p.HW - r_lo));
+  const int gpc = p.cc / p.cpg;
+  const int v = tid % p.vpc, rr = tid / p.vpc;
+  const bool active = rr < p.R;
+  const int c0 = c_lo + v * 8;   // first of this thread's 8 channels (virtual concat space)
+  uint4 reg[kItems];
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  const long long m0 = static_cast<long long>(t) * p.HW + r_lo;
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int r = rr + j * p.R;
+    if (active && r < rows) reg[j] = load_cat8(p.x1, p.C1, p.ld1, p.x2, p.ld2, m0 + r, c0);
+    else reg[j] = make_uint4(0u, 0u, 0u, 0u);
+  }
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    float f[8];
+    unpack8(reg[j], f);   // rows beyond the patch were zero-filled: they add nothing
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+  }
+  // Fixed-order tree (no atomics: hundreds of threads adding into one or two shared addresses serialise, and the result
+  // would depend on the order): thread partials -> table -> per-channel sums over the row lanes -> per-group sums.
+  float* ts = tab;
+  float* tq = tab + p.R * p.cc;
+  if (active) {
+    float4* ds = reinterpret_cast<float4*>(ts + rr * p.cc + v * 8);
+    float4* dq = reinterpret_cast<float4*>(tq + rr * p.cc + v * 8);
+    ds[0] = make_float4(s[0], s[1], s[2], s[3]); ds[1] = make_float4(s[4], s[5], s[6], s[7]);
+    dq[0] = make_float4(q[0], q[1], q[2], q[3]); dq[1] = make_float4(q[4], q[5], q[6], q[7]);
+  }
+  __syncthreads();
+  for (int c = tid; c < p.cc; c += blockDim.x) {
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+    int r = 0;
+    for (; r + 1 < p.R; r += 2) {
+      a0 += ts[r * p.cc + c]; a1 += ts[(r + 1) * p.cc + c];
+      b0 += tq[r * p.cc + c]; b1 += tq[(r + 1) * p.cc + c];
+    }
+    if (r < p.R) { a0 += ts[r * p.cc + c]; b0 += tq[r * p.cc + c]; }
+    chs[c] = a0 + a1; chs[kGnFusedThreads + c] = b0 + b1;
+  }
+  __syncthreads();
+  if (tid < gpc) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < p.cpg; ++i) { a += chs[tid * p.cpg + i]; b += chs[kGnFusedThreads + tid * p.cpg + i]; }
+    part[2 * tid] = a; part[2 * tid + 1] = b;
+  }
+  __syncthreads();
+  if (p.cs > 1) cluster_sync_all();   // every CTA's partials are complete and visible cluster-wide
+  if (tid < gpc) {
+    double sum = 0.0, sq = 0.0;
+    if (p.cs > 1) {
+      for (int k = 0; k < p.cs; ++k) {
+        sum += (double)ld_shared_cluster_f32(mapa_shared(smem_u32(&part[2 * tid]), k));
+        sq += (double)ld_shared_cluster_f32(mapa_shared(smem_u32(&part[2 * tid + 1]), k));
+      }
+    } else {
+      sum = part[2 * tid]; sq = part[2 * tid + 1];
+    }
+    const double count = (double)p.HW * p.cpg;
+    const double mean = sum / count;
+    double var = sq / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float mf = (float)mean, rf = (float)(1.0 / sqrt(var + p.eps));
+    stat[2 * tid] = mf; stat[2 * tid + 1] = rf;
+    if (p.stats_out && rank == 0) {
+      float* so = p.stats_out + (static_cast<long long>(t) * p.G + c_lo / p.cpg + tid) * 2;
+      so[0] = mf; so[1] = rf;
+    }
+  }
+  __syncthreads();
+  if (p.cs > 1) cluster_sync_all();   // nobody leaves (or reuses `part`) while a peer may still be reading it
+  if (!p.out || !active) return;
+
+  float sc[8], sh[8];   // y = x * sc + sh
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int g = (v * 8 + i) / p.cpg;
+    const float mean = stat[2 * g], rstd = stat[2 * g + 1];
+    const float ga = p.gamma ? __ldg(p.gamma + c0 + i) : 1.f, be = p.gamma ? __ldg(p.beta + c0 + i) : 0.f;
+    sc[i] = rstd * ga;
+    sh[i] = fmaf(-mean, sc[i], be);
+  }
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int r = rr + j * p.R;
+    if (r < rows) {
+      float f[8];
+      unpack8(reg[j], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float y = fmaf(f[i], sc[i], sh[i]);
+        if (p.silu) y = y / (1.f + __expf(-y));
+        f[i] = y;
+      }
+      *reinterpret_cast<uint4*>(p.out + (m0 + r) * p.ldo + c0) = pack8(f);
+    }
+  }
+}
+
 // LayerNorm over the last dim, one warp per row (C <= 2048, multiple of 8)
 constexpr int kLnMaxVec = 8;  // vectors of 8 per lane
 __global__ void layernorm_kernel(const __half* __restrict__ x, int ldx, int M, int C, const float* __restrict__ gamma,
@@ -277,6 +422,79 @@ extern "C" int mgld_gn_apply_f16(const void* x1, int C1, int ld1, const void* x2
       (const __half*)x1, C1, ld1 > 0 ? ld1 : C1, (const __half*)x2, C2, ld2 > 0 ? ld2 : C2, HW, groups, sums, eps,
       gamma, beta, silu, (__half*)out, ldo > 0 ? ldo : C);
   MGLD_LAUNCH_CHECK("gn_apply_kernel");
+  return MGLD_OK;
+}
+
+// plan of the single-launch GroupNorm; false = the patch does not fit in registers (use the multi-pass kernels)
+static bool gn_fused_plan(int C, int T, int HW, int G, GnFusedParams* p, int* items, int* csplit) {
+  if (C % 8 || G <= 0 || C % G) return false;
+  // Measured (profiles/r01_perf_norm.log): one CTA per SM holding its patch in registers serialises load -> reduce ->
+  // cluster barrier -> store, so for the 32x32 / 64x64 maps the two streaming kernels win; for <= 16x16 maps (latency-
+  // bound, 3 launches -> 1) the single launch is 25-45% faster.
+  if (HW > 256) return false;
+  const int cpg = C / G;
+  int a = 8, b = cpg;
+  while (b) { const int r = a % b; a = b; b = r; }
+  const int L = 8 / a * cpg;   // lcm(8, cpg): whole groups and whole 16-byte vectors
+  if (C % L) return false;
+  int cc = L;
+  while (cc < 64 && C % (cc * 2) == 0) cc *= 2;
+  if (cc / cpg > kGnFusedMaxGroups || cc > kGnFusedThreads) return false;
+  const int vpc = cc / 8, R = kGnFusedThreads / vpc;
+  auto need = [&](int cs) { return ceil_div(ceil_div(HW, cs), R); };
+  int cs = 1;
+  while (cs < 8 && need(cs) > 12) cs *= 2;
+  if (need(cs) > 12) return false;
+  const int ctas = T * (C / cc);
+  while (cs < 8 && ctas * cs < num_sms() && need(cs) > 1) cs *= 2;   // spread a small problem over the machine
+  p->cpg = cpg; p->cc = cc; p->vpc = vpc; p->R = R; p->cs = cs; p->rp = ceil_div(HW, cs);
+  *items = need(cs); *csplit = C / cc;
+  return true;
+}
+
+extern "C" int mgld_group_norm_fused_supported(int C, int T, int HW, int groups) {
+  GnFusedParams p;
+  int items, csplit;
+  return initialised() && gn_fused_plan(C, T, HW, groups, &p, &items, &csplit) ? 1 : 0;
+}
+
+extern "C" int mgld_group_norm_f16(const void* x1, int C1, int ld1, const void* x2, int C2, int ld2, int T, int HW,
+                                   int groups, double eps, const float* gamma, const float* beta, int silu, void* out,
+                                   int ldo, float* stats_out, double* scratch, void* stream) {
+  const int C = C1 + C2;
+  MGLD_CHECK_ARG(x1 && (out || stats_out) && T > 0 && HW > 0 && groups > 0, "group_norm: bad arguments");
+  MGLD_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0 && C % groups == 0 && (!out || ldo % 8 == 0), "group_norm: C1=%d C2=%d G=%d", C1, C2, groups);
+  MGLD_CHECK_ARG((C2 > 0) == (x2 != nullptr) && ((gamma != nullptr) == (beta != nullptr)), "group_norm: x2/C2 or gamma/beta mismatch");
+  GnFusedParams p;
+  memset(&p, 0, sizeof(p));
+  int items = 0, csplit = 0;
+  if (!gn_fused_plan(C, T, HW, groups, &p, &items, &csplit)) {
+    // multi-pass path: the caller's zeroed scratch ([T, groups, 2] doubles) carries the sums between the kernels
+    MGLD_CHECK_ARG(scratch, "group_norm: this shape needs the [T, groups, 2] fp64 scratch (zeroed)");
+    int rc = mgld_gn_stats_f16(x1, C1, ld1, x2, C2, ld2, T, HW, groups, scratch, stream);
+    if (rc) return rc;
+    if (stats_out) { rc = mgld_gn_finalize(scratch, stats_out, T, groups, HW, C, eps, stream); if (rc) return rc; }
+    if (out) rc = mgld_gn_apply_f16(x1, C1, ld1, x2, C2, ld2, T, HW, groups, scratch, eps, gamma, beta, silu, out, ldo, stream);
+    return rc;
+  }
+  p.x1 = (const __half*)x1; p.C1 = C1; p.ld1 = ld1 > 0 ? ld1 : C1;
+  p.x2 = (const __half*)x2; p.C2 = C2; p.ld2 = ld2 > 0 ? ld2 : C2;
+  p.HW = HW; p.G = groups; p.eps = eps; p.gamma = gamma; p.beta = beta; p.silu = silu;
+  p.out = (__half*)out; p.ldo = ldo; p.stats_out = stats_out;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3(p.cs, csplit, T);
+  cfg.blockDim = dim3(p.vpc * p.R, 1, 1);
+  cfg.dynamicSmemBytes = 2 * p.R * p.cc * sizeof(float);   // <= 32 KB (R * cc <= 512 * 8)
+  cfg.stream = (cudaStream_t)stream;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (items <= 2) MGLD_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_kernel<2>, p));
+  else if (items <= 4) MGLD_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_kernel<4>, p));
+  else if (items <= 8) MGLD_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_kernel<8>, p));
+  else MGLD_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_kernel<12>, p));
+  MGLD_LAUNCH_CHECK("gn_fused_kernel");
   return MGLD_OK;
 }
 

@@ -246,11 +246,54 @@ def _thwc(x):
     return T, HW, C, ld
 
 
+class _SumsPool:
+    """Zeroed fp64 [T, groups, 2] slots for the multi-pass GroupNorm statistics: ONE memset per forward (reset()) instead
+    of a zero-fill launch per normalisation.  A slot that was handed out since the last reset is zeroed on re-use.
+    Buffers are kept per (T, groups, device) and never freed: captured CUDA graphs keep writing to their addresses."""
+    SLOTS = 192
+
+    def __init__(self):
+        self.bufs = {}   # key -> [buffer, next index, dirty flags]
+
+    def reset(self):
+        for ent in self.bufs.values():
+            if any(ent[2]):
+                ent[0].zero_()
+                _count(1)
+                ent[2] = [False] * self.SLOTS
+            ent[1] = 0
+
+    def get(self, T, groups, device):
+        key = (T, groups, torch.device(device))
+        ent = self.bufs.get(key)
+        if ent is None:
+            ent = [torch.zeros(self.SLOTS, T, groups, 2, device=device, dtype=torch.float64), 0, [False] * self.SLOTS]
+            self.bufs[key] = ent
+        if ent[1] >= self.SLOTS:
+            ent[1] = 0
+        i = ent[1]
+        slot = ent[0][i]
+        if ent[2][i]:
+            slot.zero_()
+            _count(1)
+        ent[2][i] = True
+        ent[1] = i + 1
+        return slot
+
+
+_sums_pool = _SumsPool()
+
+
+def stats_pool_reset():
+    """call at the start of a model forward (inside any CUDA-graph capture of it)"""
+    _sums_pool.reset()
+
+
 def gn_stats(x1, x2=None, groups=32):
     """-> double sums [T, groups, 2] over the virtual concat [x1 | x2] (NHWC fp16)."""
     T, HW, C1, ld1 = _thwc(x1)
     C2, ld2 = (x2.shape[-1], x2.stride(-2)) if x2 is not None else (0, 0)
-    sums = torch.zeros(T, groups, 2, device=x1.device, dtype=torch.float64)
+    sums = _sums_pool.get(T, groups, x1.device)
     _count(1)
     _L.check(_L.lib().mgld_gn_stats_f16(_L.ptr(x1), C1, ld1, _L.ptr(x2), C2, ld2, T, HW, groups, _L.ptr(sums),
                                         _L.stream_ptr()))
@@ -274,6 +317,28 @@ def gn_apply(x1, sums, eps, gamma, beta, silu, x2=None, groups=32):
                                         ctypes.c_double(eps), _L.ptr(gamma), _L.ptr(beta), int(silu), _L.ptr(out),
                                         C1 + C2, _L.stream_ptr()))
     return out
+
+
+def group_norm(x1, gamma, beta, eps, silu, x2=None, groups=32, want_out=True, want_stats=False):
+    """GroupNorm [+SiLU] over the virtual concat [x1 | x2] in one call (one launch where the patch fits in registers).
+    Returns the normalised tensor, the (mean, rstd) fp32 [T, groups, 2] statistics, or both (out, stats)."""
+    T, HW, C1, ld1 = _thwc(x1)
+    C2, ld2 = (x2.shape[-1], x2.stride(-2)) if x2 is not None else (0, 0)
+    C = C1 + C2
+    out = torch.empty(*x1.shape[:-1], C, device=x1.device, dtype=torch.float16) if want_out else None
+    stats = torch.empty(T, groups, 2, device=x1.device, dtype=torch.float32) if want_stats else None
+    l = _L.lib()
+    scratch = None
+    if not l.mgld_group_norm_fused_supported(C, T, HW, groups):
+        scratch = _sums_pool.get(T, groups, x1.device)
+        _count(int(want_out) + int(want_stats))
+    _count(1)
+    _L.check(l.mgld_group_norm_f16(_L.ptr(x1), C1, ld1, _L.ptr(x2), C2, ld2, T, HW, groups, ctypes.c_double(eps),
+                                   _L.ptr(gamma), _L.ptr(beta), int(silu), _L.ptr(out), C, _L.ptr(stats),
+                                   _L.ptr(scratch), _L.stream_ptr()))
+    if want_out and want_stats:
+        return out, stats
+    return out if want_out else stats
 
 
 def layernorm(x, gamma, beta, eps=1e-5):

@@ -206,6 +206,7 @@ class RAFT_SR(_ModuleBase):
         assert ref.size() == sup.size()                                   # raft_arch.py:800
         assert flow_init is None
         ops = self.ops
+        ops.stats_pool_reset()
         ht, wd = ref.shape[-2:]
         pad_ht, pad_wd = (((ht // 8) + 1) * 8 - ht) % 8, (((wd // 8) + 1) * 8 - wd) % 8
         pad = [pad_wd // 2, pad_wd - pad_wd // 2, pad_ht // 2, pad_ht - pad_ht // 2]       # InputPadder 'sintel'

@@ -107,9 +107,9 @@ def _tag(t, sums):
 
 def _gn_silu(ops, x, gb, eps, silu=True, x2=None):
     sums = getattr(x, "_gn_sums", None) if x2 is None else None
-    if sums is None:
-        sums = ops.gn_stats(x, x2)
-    return ops.gn_apply(x, sums, eps, gb[0], gb[1], silu, x2=x2)
+    if sums is not None:   # statistics came with the producer (FUSE_GN_STATS)
+        return ops.gn_apply(x, sums, eps, gb[0], gb[1], silu, x2=x2)
+    return ops.group_norm(x, gb[0], gb[1], eps, silu, x2=x2)
 
 
 class _ResBlock:
@@ -148,7 +148,8 @@ class _ResBlock:
         s2 = pool.next() if pool is not None else None
         h2 = ops.conv_gemm(a2, self.w2, taps=TAPS_3X3, bias=self.b2, stats_out=s2)
         T, H, W, C = h2.shape
-        st = ops.gn_finalize(s2 if s2 is not None else ops.gn_stats(h2), H * W, C, 1e-5)
+        st = ops.gn_finalize(s2, H * W, C, 1e-5) if s2 is not None else \
+            ops.group_norm(h2, None, None, 1e-5, False, want_out=False, want_stats=True)
         actv = ops.conv_gemm(seg, self.ws, taps=TAPS_3X3, bias=self.bs, act=ACT_RELU)
         return _tag(ops.conv_gemm(actv, self.wgb, taps=TAPS_3X3, bias=self.bgb, epilogue=EPI_SPADE, h=h2, gn_stats=st,
                                   gn_weight=self.sn[0], gn_bias=self.sn[1], groups=32, res=sk, beta=1.0, stats_out=so), so)
@@ -529,6 +530,7 @@ class InflatedUNetModelDualcondV2(_ModuleBase):
         assert y is None, "class-conditional models are not supported"
         ops = self.ops
         self.pool.reset(x.shape[0], x.device)
+        ops.stats_pool_reset()
         seg = {int(k): as_nhwc_f16(v, ops) for k, v in struct_cond.items()}
         emb = self.time_embed(ops, _t_scalar(timesteps, x.device))
         emb_bias = self.emb.run(ops, emb)
@@ -689,6 +691,7 @@ class InflatedEncoderUNetModelWT(_ModuleBase):
         assert self.loaded, "load_state_dict() first"
         ops = self.ops
         self.pool.reset(x.shape[0], x.device)
+        ops.stats_pool_reset()
         emb_bias = self.emb.run(ops, self.time_embed(ops, _t_scalar(timesteps, x.device)))
         results, h = [], x.float().contiguous()
         for mods in self.blocks:

@@ -116,6 +116,10 @@ def _cat(x1, x2):
     return x1 if x2 is None else torch.cat([x1, x2], dim=-1)
 
 
+def stats_pool_reset():
+    pass
+
+
 def gn_stats(x1, x2=None, groups=32):
     x = _cat(x1, x2).double()
     T, C = x.shape[0], x.shape[-1]
@@ -147,6 +151,18 @@ def gn_apply(x1, sums, eps, gamma, beta, silu, x2=None, groups=32):
     if silu:
         y = F.silu(y)
     return y.half()
+
+
+def group_norm(x1, gamma, beta, eps, silu, x2=None, groups=32, want_out=True, want_stats=False):
+    sums = gn_stats(x1, x2, groups)
+    T = x1.shape[0]
+    C = x1.shape[-1] + (x2.shape[-1] if x2 is not None else 0)
+    HW = x1.numel() // (T * x1.shape[-1])
+    out = gn_apply(x1, sums, eps, gamma, beta, silu, x2=x2, groups=groups) if want_out else None
+    stats = gn_finalize(sums, HW, C, eps) if want_stats else None
+    if want_out and want_stats:
+        return out, stats
+    return out if want_out else stats
 
 
 def layernorm(x, gamma, beta, eps=1e-5):

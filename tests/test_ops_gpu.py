@@ -188,6 +188,27 @@ def test_groupnorm(T, HW, C1, C2):
     assert rel_err(O.gn_finalize(sums, HW, C1 + C2, 1e-5), E.gn_finalize(sums, HW, C1 + C2, 1e-5)) < 1e-5
 
 
+@pytest.mark.parametrize("T,HW,C1,C2", [(5, 4096, 320, 0), (5, 4096, 640, 320), (5, 1024, 1280, 640), (2, 64, 64, 0),
+                                       (3, 900, 128, 128), (5, 256, 2560, 0), (1, 64, 1280, 0), (5, 4096, 320, 320),
+                                       (1, 65536, 128, 0)])   # the last one exceeds the register patch: multi-pass path
+def test_group_norm_single_launch(T, HW, C1, C2):
+    """mgld_group_norm_f16 (cluster / DSMEM reduction, data kept in registers) against the torch emulation"""
+    O = ops()
+    x1 = (rnd(T, HW, C1) * 2 + 0.5).half()
+    x2 = rnd(T, HW, C2).half() if C2 else None
+    g, b = rnd(C1 + C2), rnd(C1 + C2, seed=2)
+    got, st = O.group_norm(x1, g, b, 1e-5, True, x2=x2, want_stats=True)
+    ref, rst = E.group_norm(x1, g, b, 1e-5, True, x2=x2, want_stats=True)
+    assert rel_err(got, ref) < 3e-3
+    assert rel_err(st, rst) < 1e-5
+    got2 = O.group_norm(x1, None, None, 1e-6, False, x2=x2)
+    assert rel_err(got2, E.group_norm(x1, None, None, 1e-6, False, x2=x2)) < 3e-3
+    st2 = O.group_norm(x1, None, None, 1e-5, False, x2=x2, want_out=False, want_stats=True)
+    assert rel_err(st2, rst) < 1e-5
+    if O._L.lib().mgld_group_norm_fused_supported(C1 + C2, T, HW, 32):   # fixed-order reduction tree: bitwise repeatable
+        assert torch.equal(got, O.group_norm(x1, g, b, 1e-5, True, x2=x2))
+
+
 @pytest.mark.parametrize("M,C", [(20480, 320), (5120, 640), (333, 1280), (7, 64)])
 def test_layernorm(M, C):
     O = ops()
