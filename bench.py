@@ -195,7 +195,8 @@ def run_reference_arm(args, cfg):
 
 def workload_config(args, world):
     return {"workload": f"{N_FRAMES_CLIP}-frame 512x512 synthetic clip per GPU (2 segments of 5 frames, last frame padded), "
-                        f"ddpm_steps={args.ddpm_steps}, SD-2.1 UNet shape (935M) + struct-cond encoder + temporal VAE, 1 UNet tile/step, "
+                        f"ddpm_steps={args.ddpm_steps}, SD-2.1 UNet shape (935M) + struct-cond encoder + temporal VAE, 1 UNet tile/step "
+                        f"per segment, the 2 independent segments sampled in lock-step as one (b t) = 10-frame UNet batch, "
                         f"RAFT flow + occlusion masks + motion guidance on (flow={args.flow})",
             "frames_per_gpu": N_FRAMES_CLIP, "global_frames": N_FRAMES_CLIP * world, "ddpm_steps": args.ddpm_steps,
             "parallelism": f"clip-per-GPU x{world} + 1 NCCL all-gather" if world > 1 else "single GPU",
@@ -309,7 +310,7 @@ def main():
     e2e_value = world * N_FRAMES_CLIP * args.steps / (ms_e2e / 1e3)
 
     # ---- roofline of the dominant kernel (conv_gemm): per-launch CUDA events over one eager tile-step -----------------
-    roofline = measure_conv_gemm_roofline(model, ops, dev, context, T)
+    roofline = measure_conv_gemm_roofline(model, ops, dev, context, T * min(pipe.clips_per_batch, n_seg))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 (fp32 accumulate; fp32 norms/softmax/schedule/guidance)", "data": "synthetic",
@@ -326,7 +327,8 @@ def main():
 
 
 def measure_conv_gemm_roofline(model, ops, dev, context, T):
-    """Every mgld_conv_gemm launch of one eager struct-encoder + UNet tile-step is bracketed by CUDA events on the
+    """Every mgld_conv_gemm launch of one eager struct-encoder + UNet tile-step (T frames = the `(b t)` batch the timed
+    workload runs per DDPM step) is bracketed by CUDA events on the
     launching stream; achieved = sum(algorithmic FLOPs) / sum(durations).  Peak: MEASURED_PEAKS.json (sustained: the
     kernel runs inside a long step), else the B200_PROFILING.md fallback."""
     peak, src = 1590.0, "fallback 1.59 PFLOP/s (B200_PROFILING.md)"
@@ -370,7 +372,7 @@ def measure_conv_gemm_roofline(model, ops, dev, context, T):
             pass
     return {"kernel": "mgld::conv_gemm_kernel (tcgen05 implicit-GEMM conv/linear)", "bound": "tensor", "achieved": achieved,
             "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "peak_source": src,
-            "launches_timed": len(rec), "flop_per_tile_step_in_kernel": tot_fl,
+            "launches_timed": len(rec), "flop_per_tile_step_in_kernel": tot_fl, "frames_per_tile_step": T,
             "note": "achieved = sum of algorithmic FLOPs of the %d conv_gemm launches of one struct-enc+UNet tile-step / "
                     "sum of their CUDA-event durations (eager launches: includes ~2 us of event/launch gap each)" % len(rec)}
 

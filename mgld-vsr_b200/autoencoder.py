@@ -257,10 +257,10 @@ class _VideoDecoder:
         self.conv_in = (P.f32(p + "conv_in.weight"), P.f32(p + "conv_in.bias"))
         self.mid1, self.attn, self.mid2 = (_ResnetBlock(P, p + "mid.block_1"), _AttnBlock(P, p + "mid.attn_1"),
                                            _ResnetBlock(P, p + "mid.block_2"))
-        self.tmix = _TemporalConv(P, p + "temporal_mixing")
+        self.tmix = _TemporalConv(P, p + "temporal_mixing", dd["num_frames"])
         self.up = {}
         for lvl in range(self.nres):
-            blocks = [(_ResnetBlock(P, f"{p}up.{lvl}.block.{b}"), _TemporalConv(P, f"{p}up.{lvl}.temporal_mixing.{b}"))
+            blocks = [(_ResnetBlock(P, f"{p}up.{lvl}.block.{b}"), _TemporalConv(P, f"{p}up.{lvl}.temporal_mixing.{b}", dd["num_frames"]))
                       for b in range(self.nrb + 1)]
             ups = _Upsample(P, f"{p}up.{lvl}.upsample") if lvl != 0 else None
             fuse = None

@@ -162,6 +162,7 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
                                linear_start=linear_start, linear_end=linear_end, cosine_s=cosine_s)
         self.ori_timesteps = None
         self._eps = _EpsRunner(self, use_graph=use_cuda_graph)
+        self.unet_clips_per_call = 2      # clips (num_frames each) batched through one struct-encoder + UNet evaluation
 
     # ---- weights (script :91-108: torch.load(ckpt)["state_dict"], strict=False) ---------------------------------------
     def load_state_dict(self, sd, strict=False):
@@ -339,22 +340,54 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
             float(h["posterior_mean_coef2"][i]), sigma)
 
     def _guidance(self, latents, flows, masks, guidance_scale, i):
-        """ddpm.py:4429-4435 with compute_temporal_condition_v4 (:3538): one fused kernel sequence."""
+        """ddpm.py:4429-4435 with compute_temporal_condition_v4 (:3538): one fused kernel sequence per clip.
+        flows (n,T-1,2,h,w) x2, masks (n,T-1,1,h,w) x2 with n clips; latents (n*T,4,h,w)."""
         flow_fwd_prop, flow_bwd_prop = flows
         fwd_occs, bwd_occs = masks
-        assert flow_fwd_prop.shape[0] == 1, "one clip per call (SURVEY.md D4)"
-        T = latents.shape[0]
+        n = flow_fwd_prop.shape[0]
+        assert latents.shape[0] % n == 0
+        T = latents.shape[0] // n
         step = float(guidance_scale) * float(self._h["posterior_log_variance_clipped"][i])
-        return self.ops.motion_guidance_f32(latents, flow_fwd_prop[0], flow_bwd_prop[0],
-                                            fwd_occs[0].reshape(T - 1, *latents.shape[-2:]),
-                                            bwd_occs[0].reshape(T - 1, *latents.shape[-2:]), step)
+        outs = [self.ops.motion_guidance_f32(latents[k * T:(k + 1) * T], flow_fwd_prop[k], flow_bwd_prop[k],
+                                             fwd_occs[k].reshape(T - 1, *latents.shape[-2:]),
+                                             bwd_occs[k].reshape(T - 1, *latents.shape[-2:]), step) for k in range(n)]
+        return outs[0] if n == 1 else torch.cat(outs, 0)
+
+    def _step_noise(self, x, num_clips):
+        """noise_like (util.py:265-268).  With several clips in the batch every clip gets the SAME draw: the inference
+        script re-seeds before each clip / VAE tile (script :428), so clips processed one after another see identical
+        noise streams - batching them must not change that."""
+        if num_clips == 1:
+            return torch.randn(x.shape, device=x.device)
+        assert x.shape[0] % num_clips == 0
+        one = torch.randn((x.shape[0] // num_clips,) + tuple(x.shape[1:]), device=x.device)
+        return one.repeat(num_clips, 1, 1, 1)
+
+    def _eps_tiles(self, x, struct_cond, t_in, context, offsets, tile_size, num_clips):
+        """eps of every UNet tile.  Tiles (and the clips inside x) are independent UNet evaluations, so up to
+        `unet_clips_per_call` clips' worth of frames go through the struct encoder + UNet as one `(b t)` batch: the
+        16x16 / 8x8 levels have too few GEMM rows per clip to fill 148 SMs."""
+        tiles = [(x[:, :, oy:oy + tile_size, ox:ox + tile_size].contiguous(),
+                  struct_cond[:, :, oy:oy + tile_size, ox:ox + tile_size].contiguous()) for (ox, oy) in offsets]
+        nf = getattr(self.model.diffusion_model, "num_frames", None)
+        whole_clips = nf is not None and x.shape[0] == num_clips * nf      # the temporal layers split `(b t)` by num_frames
+        assert num_clips == 1 or whole_clips, "num_clips > 1 needs clips of exactly num_frames frames"
+        per_call = max(1, int(self.unet_clips_per_call) // num_clips) if whole_clips else 1
+        if per_call == 1 or len(tiles) == 1:
+            return [self._eps(xt, ct, t_in[:1], context) for xt, ct in tiles]
+        out = []
+        for g in range(0, len(tiles), per_call):
+            grp = tiles[g:g + per_call]
+            eps = self._eps(torch.cat([a for a, _ in grp], 0), torch.cat([b for _, b in grp], 0), t_in[:1], context)
+            out += list(eps.chunk(len(grp), 0))
+        return out
 
     # ---- canvas sampler (ddpm.py:4383-4440, 4191-4322) -------------------------------------------------------------------
     def p_sample_canvas(self, x, c, struct_cond, t, guidance_scale=-1.0, lr_images=None, flows=None, masks=None,
                         clip_denoised=False, repeat_noise=False, return_codebook_ids=False, quantize_denoised=False,
                         return_x0=False, temperature=1.0, noise_dropout=0.0, score_corrector=None,
                         corrector_kwargs=None, t_replace=None, tile_size=64, tile_overlap=32, batch_size=4,
-                        tile_weights=None, _step=None):
+                        tile_weights=None, _step=None, num_clips=1):
         assert tile_weights is not None
         assert not (clip_denoised or quantize_denoised or return_codebook_ids or return_x0 or repeat_noise) \
             and lr_images is None and score_corrector is None and noise_dropout == 0.0 and temperature == 1.0, \
@@ -364,12 +397,8 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
         context = self._context(c)
         _, _, h, w = x.shape
         offsets = self._tile_offsets(h, w, tile_size, tile_overlap)
-        eps_tiles = []
-        for (ox, oy) in offsets:
-            xt = x[:, :, oy:oy + tile_size, ox:ox + tile_size].contiguous()
-            ct = struct_cond[:, :, oy:oy + tile_size, ox:ox + tile_size].contiguous()
-            eps_tiles.append(self._eps(xt, ct, t_in[:1], context))
-        noise = torch.randn(x.shape, device=x.device)                 # noise_like, util.py:265-268
+        eps_tiles = self._eps_tiles(x, struct_cond, t_in, context, offsets, tile_size, num_clips)
+        noise = self._step_noise(x, num_clips)                        # noise_like, util.py:265-268
         latents = self._posterior_step(x, eps_tiles, offsets, tile_size, tile_weights[0, 0].contiguous(), i, noise)
         if flows is not None:
             latents = self._guidance(latents, flows, masks, guidance_scale, i)
@@ -379,7 +408,7 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
                              masks=None, return_intermediates=False, x_T=None, verbose=True, callback=None,
                              timesteps=None, quantize_denoised=False, mask=None, x0=None, img_callback=None,
                              start_T=None, log_every_t=None, time_replace=None, adain_fea=None, interfea_path=None,
-                             tile_size=64, tile_overlap=32, batch_size=4):
+                             tile_size=64, tile_overlap=32, batch_size=4, num_clips=1):
         assert tile_size is not None
         assert mask is None and adain_fea is None and interfea_path is None, "option not used by the VSR path"
         log_every_t = log_every_t or self.log_every_t
@@ -400,7 +429,7 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
                                        flows=flows, masks=masks, clip_denoised=self.clip_denoised,
                                        quantize_denoised=quantize_denoised, t_replace=t_replace, tile_size=tile_size,
                                        tile_overlap=tile_overlap, batch_size=batch_size, tile_weights=tile_weights,
-                                       _step=i)
+                                       _step=i, num_clips=num_clips)
             if i % log_every_t == 0 or i == timesteps - 1:
                 intermediates.append(img)
             if callback:
@@ -414,8 +443,10 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
                       batch_size=16, return_intermediates=False, x_T=None, verbose=True, timesteps=None,
                       quantize_denoised=False, mask=None, x0=None, shape=None, time_replace=None, adain_fea=None,
                       interfea_path=None, tile_size=64, tile_overlap=32, batch_size_sample=4, log_every_t=None,
-                      **kwargs):
-        """ddpm.py:4722-4760"""
+                      num_clips=1, **kwargs):
+        """ddpm.py:4722-4760.  `num_clips` (extension; the reference only works with one clip per call):
+        x_T / struct_cond hold num_clips * num_frames frames, flows / masks have num_clips rows, and every clip is
+        sampled exactly as if it had been passed alone after the script's per-clip re-seed (script :428)."""
         if batch_size_sample != 1:
             raise NotImplementedError("batch_size_sample > 1 mis-indexes tiles in the reference (SURVEY.md D5)")
         if shape is None:
@@ -426,7 +457,7 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
                                          timesteps=timesteps, quantize_denoised=quantize_denoised, mask=mask, x0=x0,
                                          time_replace=time_replace, adain_fea=adain_fea, interfea_path=interfea_path,
                                          tile_size=tile_size, tile_overlap=tile_overlap, batch_size=batch_size_sample,
-                                         log_every_t=log_every_t)
+                                         log_every_t=log_every_t, num_clips=num_clips)
 
     # ---- untiled sampler (ddpm.py:4325-4381, 4501-4599, 4696-4720) ----------------------------------------------------
     def p_sample_loop(self, cond, struct_cond, shape, guidance_scale=-1.0, lr_images=None, flows=None, masks=None,

@@ -104,11 +104,14 @@ def wavelet_reconstruction(content_feat, style_feat, levels=5):
 
 class VSRPipeline:
     def __init__(self, model, vq_model, ddpm_steps=50, n_frames=5, upscale=4.0, vqgantile_size=960,
-                 vqgantile_stride=750, tile_overlap=32, colorfix_type="adain", seed=42, dec_w=1.0, guidance_scale=-10.0):
+                 vqgantile_stride=750, tile_overlap=32, colorfix_type="adain", seed=42, dec_w=1.0, guidance_scale=-10.0,
+                 clips_per_batch=2, input_size=512):
         self.model, self.vq = model, vq_model
         self.S, self.n_frames, self.upscale = ddpm_steps, n_frames, upscale
         self.tile, self.stride, self.tile_overlap = vqgantile_size, vqgantile_stride, tile_overlap
         self.colorfix, self.seed, self.guidance_scale = colorfix_type, seed, guidance_scale
+        self.clips_per_batch = clips_per_batch     # independent units (segments / VAE tiles) sampled in lock-step
+        self.latent_tile = int(input_size / 8)     # script :450 tile_size=int(opt.input_size/8), --input_size 512
         if getattr(vq_model, "decoder", None) is not None:
             vq_model.decoder.fusion_w = dec_w                                     # script :306
         self.sqrt_ac, self.sqrt_1m_ac = model.respace(ddpm_steps)                # script :308-328
@@ -136,16 +139,18 @@ class VSRPipeline:
             lq01 = torch.clamp((im_lq_bs + 1.0) / 2.0, min=0.0, max=1.0)
             lq01 = F.interpolate(lq01, size=(im_h // 4, im_w // 4), mode="bicubic")[None]
             flows = self.model.compute_flow(lq01)
-            flows = [resize_flow(f[0], "shape", (im_h // 8, im_w // 8)) for f in flows]
+            flows = [resize_flow(f[0], "shape", (im_h // 8, im_w // 8), ops=self.model.ops) for f in flows]
         fo, bo = [], []
         for i in range(T - 1):
-            a, b = forward_backward_consistency_check(flows[1][i:i + 1], flows[0][i:i + 1], alpha=0.01, beta=0.5)
+            a, b = forward_backward_consistency_check(flows[1][i:i + 1], flows[0][i:i + 1], alpha=0.01, beta=0.5,
+                                                      ops=self.model.ops)
             fo.append(a[:, None])
             bo.append(b[:, None])
         return flows, (torch.cat(fo, 0), torch.cat(bo, 0))
 
-    def _sr_tile(self, im_lq_pch, flow_f, flow_b, fwd_occ, bwd_occ, context):
-        """one VAE tile of one segment: script :428-473"""
+    # ---- one unit of work = one VAE tile of one segment: script :428-473 --------------------------------------------
+    def _prepare_unit(self, im_lq_pch):
+        """script :428-440: re-seed, LR latent (struct cond) and the noised start x_T."""
         m, T = self.model, im_lq_pch.shape[0]
         torch.manual_seed(self.seed)                                              # seed_everything per tile (:428)
         init_latent = m.get_first_stage_encoding(m.encode_first_stage(im_lq_pch))
@@ -153,22 +158,55 @@ class VSRPipeline:
         t = torch.full((T,), 999, device=im_lq_pch.device, dtype=torch.long)
         x_T = m.q_sample_respace(x_start=init_latent, t=t, sqrt_alphas_cumprod=self.sqrt_ac,
                                  sqrt_one_minus_alphas_cumprod=self.sqrt_1m_ac, noise=noise)
-        flows = (flow_f[None], flow_b[None]) if flow_f is not None else None
-        masks = (fwd_occ[None], bwd_occ[None]) if flow_f is not None else None
-        samples = m.sample_canvas(cond=context, struct_cond=init_latent, guidance_scale=self.guidance_scale,
-                                  flows=flows, masks=masks, batch_size=T, timesteps=self.S, time_replace=self.S,
-                                  x_T=x_T, tile_size=64, tile_overlap=self.tile_overlap, batch_size_sample=1)
+        return init_latent, x_T
+
+    def _finish_unit(self, samples, im_lq_pch):
+        """script :465-473: temporal VAE decode with the LR encoder taps, colour fix."""
         _, enc_fea = self.vq.encode(im_lq_pch)
-        x = self.vq.decode(samples * (1.0 / m.scale_factor), enc_fea)
+        x = self.vq.decode(samples * (1.0 / self.model.scale_factor), enc_fea)
         if self.colorfix == "adain":
             x = adaptive_instance_normalization(x, im_lq_pch)
         elif self.colorfix == "wavelet":
             x = wavelet_reconstruction(x, im_lq_pch)
         return x
 
-    @torch.no_grad()
-    def super_resolve_segment(self, init_image, context, flows_override=None, use_guidance=True):
-        """script :375-535 for one (T,3,H,W) segment -> (T,3,H',W') in [0,1]"""
+    def _sr_units(self, units, context):
+        """units: [(im_lq_pch, flow_f, flow_b, fwd_occ, bwd_occ)] -> [decoded tile].  Units are independent (the script
+        re-seeds before each one), so up to `clips_per_batch` units of equal shape are sampled in lock-step as one
+        `(b t)` batch; each unit's result is what it would be if it had been processed alone."""
+        m = self.model
+        out = [None] * len(units)
+        todo = list(range(len(units)))
+        while todo:
+            shape0 = units[todo[0]][0].shape
+            has_flow0 = units[todo[0]][1] is not None
+            grp = [i for i in todo if units[i][0].shape == shape0 and (units[i][1] is not None) == has_flow0]
+            grp = grp[:max(1, self.clips_per_batch)]
+            todo = [i for i in todo if i not in grp]
+            T = shape0[0]
+            prep = [self._prepare_unit(units[i][0]) for i in grp]
+            init_latent = torch.cat([p[0] for p in prep], 0)
+            x_T = torch.cat([p[1] for p in prep], 0)
+            if has_flow0:
+                flows = tuple(torch.stack([units[i][j] for i in grp], 0) for j in (1, 2))
+                masks = tuple(torch.stack([units[i][j] for i in grp], 0) for j in (3, 4))
+            else:
+                flows = masks = None
+            samples = m.sample_canvas(cond=context, struct_cond=init_latent, guidance_scale=self.guidance_scale,
+                                      flows=flows, masks=masks, batch_size=T, timesteps=self.S, time_replace=self.S,
+                                      x_T=x_T, tile_size=self.latent_tile, tile_overlap=self.tile_overlap,
+                                      batch_size_sample=1, **({"num_clips": len(grp)} if len(grp) > 1 else {}))
+            for k, i in enumerate(grp):
+                out[i] = self._finish_unit(samples[k * T:(k + 1) * T], units[i][0])
+        return out
+
+    def _sr_tile(self, im_lq_pch, flow_f, flow_b, fwd_occ, bwd_occ, context):
+        """one VAE tile of one segment: script :428-473"""
+        return self._sr_units([(im_lq_pch, flow_f, flow_b, fwd_occ, bwd_occ)], context)[0]
+
+    # ---- script :375-535 for one segment, split into "cut into units" and "assemble" so that units of several segments
+    # can be batched --------------------------------------------------------------------------------------------------
+    def _segment_units(self, init_image, flows_override=None, use_guidance=True):
         im = init_image.clamp(-1.0, 1.0)
         ori_h, ori_w = im.shape[2:]
         flag_pad = not (ori_h % 32 == 0 and ori_w % 32 == 0)
@@ -178,24 +216,40 @@ class VSRPipeline:
             flows, (fwd_occs, bwd_occs) = self.estimate_flows(im, flows_override)
         else:
             flows, fwd_occs, bwd_occs = [None, None], None, None
+        sp, units, infos = None, [], []
         if im.shape[2] > self.tile or im.shape[3] > self.tile:
             sp = ImageSpliterTh(im, self.tile, self.stride, sf=1)
             aux = [ImageSpliterTh(t, self.tile // 8, self.stride // 8, sf=1) if t is not None else None
                    for t in (flows[0], flows[1], fwd_occs, bwd_occs)]               # quirk D10: 750 // 8 = 93
             for pch, index_infos in sp:
-                parts = [next(a)[0] if a is not None else None for a in aux]
-                sp.update(self._sr_tile(pch, *parts, context), index_infos)
+                units.append((pch, *[next(a)[0] if a is not None else None for a in aux]))
+                infos.append(index_infos)
+        else:
+            units.append((im, flows[0], flows[1], fwd_occs, bwd_occs))            # D2 resolved
+        return dict(im=im, ori=(ori_h, ori_w), flag_pad=flag_pad, sp=sp, infos=infos), units
+
+    def _segment_assemble(self, meta, tiles):
+        im, sp = meta["im"], meta["sp"]
+        if sp is not None:
+            for x, index_infos in zip(tiles, meta["infos"]):
+                sp.update(x, index_infos)
             x = sp.gather()
         else:
-            x = self._sr_tile(im, flows[0], flows[1], fwd_occs, bwd_occs, context)   # D2 resolved
+            x = tiles[0]
         im_sr = torch.clamp((x + 1.0) / 2.0, min=0.0, max=1.0)
         if self.upsample_scale > self.upscale:
             im_sr = F.interpolate(im_sr, size=(int(im.size(-2) * self.upscale / self.upsample_scale),
                                                int(im.size(-1) * self.upscale / self.upsample_scale)), mode="bicubic")
             im_sr = torch.clamp(im_sr, min=0.0, max=1.0)
-        if flag_pad:
-            im_sr = im_sr[:, :, :ori_h, :ori_w]
+        if meta["flag_pad"]:
+            im_sr = im_sr[:, :, :meta["ori"][0], :meta["ori"][1]]
         return im_sr
+
+    @torch.no_grad()
+    def super_resolve_segment(self, init_image, context, flows_override=None, use_guidance=True):
+        """script :375-535 for one (T,3,H,W) segment -> (T,3,H',W') in [0,1]"""
+        meta, units = self._segment_units(init_image, flows_override, use_guidance)
+        return self._segment_assemble(meta, self._sr_units(units, context))
 
     @torch.no_grad()
     def __call__(self, frames, context=None, flows_override=None, use_guidance=True):
@@ -203,10 +257,16 @@ class VSRPipeline:
         if context is None:
             context = self.model.cond_stage_model([""])
         segs, n = self.segments(frames)
-        outs = []
+        metas, units, owner = [], [], []
         for si, seg in enumerate(segs):
             fo = None if flows_override is None else flows_override[si]
-            outs.append(self.super_resolve_segment(seg, context, fo, use_guidance))
+            meta, u = self._segment_units(seg, fo, use_guidance)
+            metas.append(meta)
+            owner += [si] * len(u)
+            units += u
+        tiles = self._sr_units(units, context)
+        outs = [self._segment_assemble(meta, [t for t, o in zip(tiles, owner) if o == si])
+                for si, meta in enumerate(metas)]
         return torch.cat(outs, 0)[:n]
 
 

@@ -250,24 +250,35 @@ class _SpatialTransformer:
 
 
 class _TemporalConv:
-    """SpatialTemporalConv, util.py:291-310: alpha * conv3d_(3,1,1)(x) + (1-alpha) * x."""
+    """SpatialTemporalConv, util.py:291-310: alpha * conv3d_(3,1,1)(x) + (1-alpha) * x.
+    x holds `(b t)` frames (b clips of `nf` frames): the temporal zero padding applies per clip, so each clip is one
+    GEMM whose TMA box loads run out of bounds at ITS first / last frame."""
 
-    def __init__(self, P, p):
+    def __init__(self, P, p, nf):
         self.w = pack_temporal_weight(P.raw(p + ".temporal_conv.weight").detach().float()).to(P.dev)
         self.b = P.f32(p + ".temporal_conv.bias")
         self.alpha = float(P.raw(p + ".temporal_alpha").detach().float().reshape(-1)[0])
+        self.nf = nf
 
     def __call__(self, ops, x, pool=None):
         so = pool.next() if pool is not None else None
-        return _tag(ops.conv_gemm(x, self.w, taps=TAPS_T3, bias=self.b, alpha=self.alpha, beta=1.0 - self.alpha, res=x,
-                                  stats_out=so), so)
+        nf = self.nf
+        if x.shape[0] <= nf:
+            return _tag(ops.conv_gemm(x, self.w, taps=TAPS_T3, bias=self.b, alpha=self.alpha, beta=1.0 - self.alpha,
+                                      res=x, stats_out=so), so)
+        assert x.shape[0] % nf == 0 and so is None, "frames must be whole clips of num_frames"
+        out = torch.empty_like(x)
+        for k in range(0, x.shape[0], nf):
+            ops.conv_gemm(x[k:k + nf], self.w, taps=TAPS_T3, bias=self.b, alpha=self.alpha, beta=1.0 - self.alpha,
+                          res=x[k:k + nf], out=out[k:k + nf])
+        return out
 
 
 class _TemporalAttention:
-    """TemporalAttention, attention.py:124-143."""
+    """TemporalAttention, attention.py:124-143: `(b t) c h w -> (b h w) t c`, attention along t within each clip."""
 
-    def __init__(self, P, p, C, heads):
-        self.heads = heads
+    def __init__(self, P, p, C, heads, nf):
+        self.heads, self.nf = heads, nf
         self.ln = P.norm(p + ".norm")
         a = p + ".temporal_attn"
         self.wqkv = torch.cat([P.f16(f"{a}.to_{n}.weight") for n in "qkv"], 0).contiguous()
@@ -276,9 +287,15 @@ class _TemporalAttention:
 
     def __call__(self, ops, x, pool=None):
         T, H, W, C = x.shape
+        nf = self.nf
         n = ops.layernorm(x.reshape(T * H * W, C), *self.ln)
         qkv = ops.conv_gemm(n, self.wqkv).reshape(T, H * W, 3 * C)
-        a = ops.temporal_attention(qkv, self.heads, (C // self.heads) ** -0.5)
+        scale = (C // self.heads) ** -0.5
+        if T <= nf:
+            a = ops.temporal_attention(qkv, self.heads, scale)
+        else:
+            assert T % nf == 0, "frames must be whole clips of num_frames"
+            a = torch.cat([ops.temporal_attention(qkv[k:k + nf], self.heads, scale) for k in range(0, T, nf)], 0)
         so = pool.next() if pool is not None else None
         out = ops.conv_gemm(a, self.wo, bias=self.bo, alpha=self.alpha, beta=1.0 - self.alpha,
                             res=x.reshape(T, H * W, C), stats_out=so)
@@ -484,9 +501,9 @@ class InflatedUNetModelDualcondV2(_ModuleBase):
             if l[0] == "st":
                 return ("st", _SpatialTransformer(P, p, l[1], l[2], self.kvc))
             if l[0] == "stconv":
-                return ("stconv", _TemporalConv(P, p))
+                return ("stconv", _TemporalConv(P, p, self.num_frames))
             if l[0] == "tattn":
-                return ("tattn", _TemporalAttention(P, p, l[1], l[2]))
+                return ("tattn", _TemporalAttention(P, p, l[1], l[2], self.num_frames))
             if l[0] == "down":
                 return ("down", _Downsample(P, p))
             if l[0] == "up":

@@ -151,3 +151,60 @@ def test_raft_vs_oracle_and_golden():
     # odd sizes exercise the replicate padding and the non-16-byte-aligned correlation rows
     a, b = torch.rand(1, 3, 130, 150, device=DEV), torch.rand(1, 3, 130, 150, device=DEV)
     assert rel_err(m(a, b, iters=3), R.raft_forward(to_dev(sd), a, b, iters=3)) < 1e-2
+
+
+def test_unet_two_clips_in_one_batch_vs_oracle():
+    """`(b t)` batch of two clips (clip batching of independent segments / tiles): against the oracle's evaluation of the
+    same batch (reference rearranges, util.py:301-310, attention.py:135-141) and against each clip run alone."""
+    from mgld_vsr_b200.unet import InflatedEncoderUNetModelWT, InflatedUNetModelDualcondV2
+    unet, se = InflatedUNetModelDualcondV2(**TINY_UNET), InflatedEncoderUNetModelWT(**TINY_STRUCT)
+    sd_u, sd_s = det_state_dict(unet.expected_shapes()), det_state_dict(se.expected_shapes())
+    unet.load_state_dict(sd_u)
+    se.load_state_dict(sd_s)
+    x, lat = det_tensor("x2", (2 * T, 4, 32, 32)).to(DEV), det_tensor("lat2", (2 * T, 4, 32, 32)).to(DEV)
+    ctx, t = det_tensor("ctx", (1, 77, 128)).to(DEV), torch.tensor([321], device=DEV)
+    both = unet(x, t, ctx, se(lat, t))
+    ref = R.unet_forward(to_dev(sd_u), TINY_UNET, x, t, ctx,
+                         R.struct_encoder_forward(to_dev(sd_s), TINY_STRUCT, lat, t, prefix=""), prefix="")
+    assert rel_err(both, ref) < 1e-2
+    for k in range(2):
+        alone = unet(x[k * T:(k + 1) * T], t, ctx, se(lat[k * T:(k + 1) * T], t))
+        assert rel_err(both[k * T:(k + 1) * T], alone) < 2e-3     # tile plans differ with the row count: fp16 rounding only
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_sample_canvas_num_clips_equals_clip_by_clip(use_graph):
+    m, _ = build_tiny_ldm(use_graph)
+    S, h, w = 2, 48, 40
+    m.respace(S)
+    ctx = det_tensor("ctx", (1, 77, 128)).to(DEV)
+    from mgld_vsr_b200.flow import forward_backward_consistency_check
+    clips = []
+    for k in range(2):
+        ff = 1.5 * F.interpolate(det_tensor(f"ff{k}", (T - 1, 2, 6, 5)), size=(h, w), mode="bicubic")[None].to(DEV)
+        fb = -ff + 0.2 * F.interpolate(det_tensor(f"fb{k}", (T - 1, 2, 6, 5)), size=(h, w), mode="bicubic")[None].to(DEV)
+        fo, bo = forward_backward_consistency_check(fb[:, 0], ff[:, 0])
+        clips.append((det_tensor(f"lat{k}", (T, 4, h, w)).to(DEV), det_tensor(f"xT{k}", (T, 4, h, w)).to(DEV),
+                      (ff, fb, fo[:, None, None], bo[:, None, None])))
+    # guidance off here: its L1 sign() turns fp16-rounding differences between tile plans into O(1) differences (D8)
+    kw = dict(cond=ctx, guidance_scale=-10.0, batch_size=T, timesteps=S, time_replace=S, tile_size=32, tile_overlap=16,
+              batch_size_sample=1)
+    alone = []
+    for lat, x_T, _ in clips:
+        torch.manual_seed(7)
+        alone.append(m.sample_canvas(struct_cond=lat, x_T=x_T, **kw))
+    torch.manual_seed(7)
+    got = m.sample_canvas(struct_cond=torch.cat([c[0] for c in clips], 0), x_T=torch.cat([c[1] for c in clips], 0),
+                          num_clips=2, **kw)
+    for k in range(2):
+        assert rel_err(got[k * T:(k + 1) * T], alone[k]) < 5e-3
+    # with guidance: runs, finite, and each clip stays close to its clip-by-clip result
+    torch.manual_seed(7)
+    got_g = m.sample_canvas(struct_cond=torch.cat([c[0] for c in clips], 0), x_T=torch.cat([c[1] for c in clips], 0),
+                            flows=tuple(torch.cat([c[2][j] for c in clips], 0) for j in (0, 1)),
+                            masks=tuple(torch.cat([c[2][j] for c in clips], 0) for j in (2, 3)), num_clips=2, **kw)
+    assert torch.isfinite(got_g).all()
+    for k, (lat, x_T, (ff, fb, fo, bo)) in enumerate(clips):
+        torch.manual_seed(7)
+        one = m.sample_canvas(struct_cond=lat, x_T=x_T, flows=(ff, fb), masks=(fo, bo), **kw)
+        assert rel_err(got_g[k * T:(k + 1) * T], one) < 2.5e-2

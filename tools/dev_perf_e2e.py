@@ -40,7 +40,7 @@ def timeit(fn, n=5, warm=2):
     return e0.elapsed_time(e1) / n
 
 what = sys.argv[1:] or ["unet", "vae"]
-T = 5
+T = int(os.environ.get("MGLD_T", "5"))   # frames per call (5 = one segment; 10 = two segments batched)
 if "unet" in what:
     t0 = time.time()
     unet = InflatedUNetModelDualcondV2(**UNET); se = InflatedEncoderUNetModelWT(**STRUCT)
@@ -51,7 +51,7 @@ if "unet" in what:
     feats = se(lat, t)
     ms_se = timeit(lambda: se(lat, t))
     ms_un = timeit(lambda: unet(x, t, ctx, feats))
-    print(f"eager: struct-enc {ms_se:.2f} ms, unet {ms_un:.2f} ms  (4.837 TFLOP -> {4.837/(ms_se+ms_un):.2f} PFLOP/s eff)", flush=True)
+    print(f"eager: struct-enc {ms_se:.2f} ms, unet {ms_un:.2f} ms  ({4.837*T/5:.3f} TFLOP -> {4.837*T/5/(ms_se+ms_un):.2f} PFLOP/s eff)", flush=True)
     # CUDA graph
     def step(): return unet(x, t, ctx, se(lat, t))
     s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
@@ -62,7 +62,7 @@ if "unet" in what:
     with torch.cuda.graph(g):
         out = step()
     ms_g = timeit(lambda: g.replay(), n=10)
-    print(f"graph: struct-enc+unet tile-step {ms_g:.2f} ms -> {4.837/ms_g:.3f} PFLOP/s ({4.837/ms_g/1.6942*100:.1f}% of measured bf16 peak)", flush=True)
+    print(f"graph: struct-enc+unet tile-step T={T}: {ms_g:.2f} ms -> {4.837*T/5/ms_g:.3f} PFLOP/s, {ms_g/T:.3f} ms/frame", flush=True)
     print("eps finite:", torch.isfinite(out).all().item(), out.abs().max().item())
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
