@@ -16,6 +16,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "../../include/mgld.h"
 #include "common.h"
 #include "ptx.cuh"
@@ -532,6 +534,342 @@ static int launch_attention_v2(const mgld_attention_desc* d, cudaStream_t stream
   return MGLD_OK;
 }
 
+
+// =====================================================================================================================
+// v3 (head_dim 64): v2's two ping-pong query tiles, restructured around what actually bounds d=64 attention on sm_100a.
+// Per 128x128 score block the tensor core needs 512 cycles (QK^T + PV) but the SM's 16 MUFU lanes need 1024 cycles for
+// the 16384 exponentials, so the softmax warps — not the MMA — set the pace, and every instruction they issue counts:
+//   * a thread loads its WHOLE score row (128 fp32) into registers with four back-to-back tcgen05.ld and one wait, and
+//     releases the S buffer at once (s_free): S_i(j+1) is computed while softmax_i(j) is still exponentiating.  P gets
+//     its own TMEM columns (fp16 pairs) instead of overwriting S, so nothing in the softmax loop waits for an MMA
+//     except the (long finished) PV of the previous block before P is overwritten;
+//   * scale-subtract and the row sum use packed fp32x2 FMA/ADD, the exponential is a bare ex2.approx, max is 3-input;
+//   * kEmu of every 8 exponentials are evaluated on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial,
+//     7.5e-5 relative error, below fp16 rounding of P) to take load off the MUFU unit;
+//   * the row sum is taken over the unrounded fp32 probabilities (what PyTorch's softmax does).
+// TMEM (512 columns): S0 S1 [0,256) | P0 P1 [256,384) | O0 O1 [384,512).  One CTA per SM, 384 threads; the softmax
+// warpgroups take the registers the TMA / MMA warpgroup gives up (setmaxnreg) so a whole score row stays in registers.
+// =====================================================================================================================
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// d = a * b + c on two fp32 lanes at once (sm_100 packed fp32)
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n.reg .b64 ra, rb, rc, rd;\n"
+      "mov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmov.b64 rc, {%6, %7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n"
+      "mov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n.reg .b64 ra, rb, rd;\n"
+      "mov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\n"
+      "add.rn.f32x2 rd, ra, rb;\n"
+      "mov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// 2^x for x in [-125, 125] on the FMA / ALU pipes: n = round(x) via the 1.5 * 2^23 trick, 2^(x - n) by a degree-3 minimax
+// polynomial on [-0.5, 0.5], exponent patched in with an integer add.  Two lanes at a time.
+__device__ __forceinline__ void exp2_poly2(float& y0, float& y1, float x0, float x1) {
+  constexpr float kMagic = 12582912.f;  // 1.5 * 2^23
+  constexpr float c0 = 0.9999280571937561f, c1 = 0.6932610273361206f, c2 = 0.2426111102104187f, c3 = 0.05517156794667244f;
+  x0 = fmaxf(x0, -125.f);
+  x1 = fmaxf(x1, -125.f);
+  float t0, t1, n0, n1, r0, r1, p0, p1;
+  fadd2(t0, t1, x0, x1, kMagic, kMagic);
+  fadd2(n0, n1, t0, t1, -kMagic, -kMagic);
+  ffma2(r0, r1, n0, n1, -1.f, -1.f, x0, x1);
+  ffma2(p0, p1, r0, r1, c3, c3, c2, c2);
+  ffma2(p0, p1, p0, p1, r0, r1, c1, c1);
+  ffma2(p0, p1, p0, p1, r0, r1, c0, c0);
+  y0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
+constexpr int kV3Threads = 384;   // warpgroup 0: TMA warp, MMA warp, two idle warps; warpgroups 1, 2: softmax of tile 0, 1
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+template <int kEmu>
+__global__ void __launch_bounds__(kV3Threads, 1)
+attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  constexpr int DH = 64;
+  constexpr int kTileBytes = 128 * DH * 2;  // 16 KB: one [128 x 64] fp16 operand tile
+  constexpr uint32_t kSCol = 0, kPCol = 256, kOCol = 384;   // + i * 128 / 64 / 64
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t q_full, kv_full[kV2Stages], kv_empty[kV2Stages], s_full[2], s_free[2], p_full[2],
+      pv_done[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem_base;                       // two tiles
+  const uint32_t sKV = sQ + 2 * kTileBytes;            // stage s: K at +s*2*kTileBytes, V after K
+
+  const int q0 = blockIdx.x * 256;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int nblk = (p.nkv + kKVTile - 1) / kKVTile;
+  const int kvb = p.kv_batched ? b : 0;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(smem_u32(&q_full), 1);
+    for (int s = 0; s < kV2Stages; ++s) { mbar_init(smem_u32(&kv_full[s]), 1); mbar_init(smem_u32(&kv_empty[s]), 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&s_free[i]), 128);
+      mbar_init(smem_u32(&p_full[i]), 128);
+      mbar_init(smem_u32(&pv_done[i]), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp < 4) {
+  setmaxnreg_dec<88>();
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(smem_u32(&q_full), 2 * kTileBytes);
+      tma_load_3d(sQ, &tmQ, smem_u32(&q_full), p.q_col0 + head * p.q_hstride, q0, b);
+      tma_load_3d(sQ + kTileBytes, &tmQ, smem_u32(&q_full), p.q_col0 + head * p.q_hstride, q0 + 128, b);
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j % kV2Stages;
+        mbar_wait(smem_u32(&kv_empty[s]), ((j / kV2Stages) & 1) ^ 1);
+        const uint32_t fb = smem_u32(&kv_full[s]);
+        mbar_expect_tx(fb, 2 * kTileBytes);
+        tma_load_3d(sKV + s * 2 * kTileBytes, &tmK, fb, p.k_col0 + head * p.k_hstride, j * kKVTile, kvb);
+        tma_load_3d(sKV + s * 2 * kTileBytes + kTileBytes, &tmV, fb, p.v_col0 + head * p.v_hstride, j * kKVTile, kvb);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc_s = umma_idesc_f16(128, kKVTile, 0, 0);
+      const uint32_t idesc_o = umma_idesc_f16(128, DH, 0, 1);  // B = V, MN-major
+      auto issue_s = [&](int i, int j) {
+        const uint32_t sk = sKV + (j % kV2Stages) * 2 * kTileBytes;
+        const uint32_t sq = sQ + i * kTileBytes;
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          umma_ss(tmem_base + kSCol + i * 128, umma_smem_desc(sq + k * 32, 0, 1024, kSwz128),
+                  umma_smem_desc(sk + k * 32, 0, 1024, kSwz128), idesc_s, k != 0);
+        umma_commit(smem_u32(&s_full[i]));
+      };
+      mbar_wait(smem_u32(&q_full), 0);
+      mbar_wait(smem_u32(&kv_full[0]), 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j % kV2Stages;
+        const uint32_t sv = sKV + s * 2 * kTileBytes + kTileBytes;
+        if (j + 1 < nblk) {
+          mbar_wait(smem_u32(&kv_full[(j + 1) % kV2Stages]), ((j + 1) / kV2Stages) & 1);   // K_{j+1} has landed
+          for (int i = 0; i < 2; ++i) {
+            mbar_wait(smem_u32(&s_free[i]), j & 1);   // softmax_i holds S_i(j) in registers: the buffer is free
+            tc_fence_after();
+            issue_s(i, j + 1);
+          }
+        }
+        for (int i = 0; i < 2; ++i) {
+          mbar_wait(smem_u32(&p_full[i]), j & 1);
+          tc_fence_after();
+          const uint32_t pcol = tmem_base + kPCol + i * 64;
+          const uint32_t ocol = tmem_base + kOCol + i * 64;
+#pragma unroll
+          for (int k = 0; k < kKVTile / 16; ++k)  // A: 16 keys = 8 packed columns per step; B: 16 key rows = 2048 B
+            umma_ts(ocol, pcol + k * 8, umma_smem_desc(sv + k * 2048, 0, 1024, kSwz128), idesc_o, (j | k) != 0);
+          umma_commit(smem_u32(&pv_done[i]));
+          if (i == 1) umma_commit(smem_u32(&kv_empty[s]));
+        }
+      }
+    }
+  }
+  } else {
+    // softmax warpgroup i: warps 4-7 -> tile 0, warps 8-11 -> tile 1; thread == query row
+    setmaxnreg_inc<208>();
+    const int i = (warp - 4) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t srow = tmem_base + lane_off + kSCol + i * 128;
+    const uint32_t prow = tmem_base + lane_off + kPCol + i * 64;
+    const uint32_t orow = tmem_base + lane_off + kOCol + i * 64;
+    const float k2 = p.scale_log2e;
+    float m_run = -INFINITY, l_run = 0.f;
+    // one 128-key block of this thread's query row.  kMasked: the last, partial block (keys beyond nkv are masked);
+    // a separate instantiation so that the full blocks carry no per-element select
+    auto block = [&](const int j, auto masked_tag) {
+      constexpr bool kMasked = decltype(masked_tag)::value;
+      mbar_wait(smem_u32(&s_full[i]), j & 1);
+      tc_fence_after();
+      float sc[kKVTile];
+#pragma unroll
+      for (int c0 = 0; c0 < kKVTile; c0 += 32) tmem_ld_x32(srow + c0, reinterpret_cast<uint32_t*>(sc) + c0);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&s_free[i]));
+      if constexpr (kMasked) {
+        const int kv_left = p.nkv - j * kKVTile;
+#pragma unroll
+        for (int u = 0; u < kKVTile; ++u)
+          if (u >= kv_left) sc[u] = -INFINITY;
+      }
+      float mx0 = sc[0], mx1 = sc[1], mx2 = sc[2], mx3 = sc[3];
+#pragma unroll
+      for (int u = 4; u < kKVTile; u += 8) {
+        mx0 = fmaxf(mx0, fmaxf(sc[u], sc[u + 1]));
+        mx1 = fmaxf(mx1, fmaxf(sc[u + 2], sc[u + 3]));
+        if (u + 4 < kKVTile) {
+          mx2 = fmaxf(mx2, fmaxf(sc[u + 4], sc[u + 5]));
+          mx3 = fmaxf(mx3, fmaxf(sc[u + 6], sc[u + 7]));
+        }
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      // lazy max update: only move the reference max when it grew by more than 8 in the exp2 domain
+      float alpha = 1.f;
+      const bool grow = (mx - m_run) * k2 > 8.f;   // also true on the first block (m_run = -inf)
+      if (grow) {
+        alpha = ex2_approx((m_run - mx) * k2);      // 0 on the first block
+        m_run = mx;
+      }
+      const float nmk = -m_run * k2;
+      if (j > 0) {
+        // PV_i(j-1) has consumed P_i and O_i is quiescent.  It was issued a full softmax block ago: this wait is free in
+        // steady state, and taking it here lets every 32-column chunk of P go to TMEM as soon as it is computed.
+        mbar_wait(smem_u32(&pv_done[i]), (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll
+          for (int c0 = 0; c0 < DH; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_x32(orow + c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 32; ++u) r[u] = __float_as_uint(__uint_as_float(r[u]) * alpha);
+            tmem_st_x32(orow + c0, r);
+          }
+        }
+      }
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < kKVTile; c0 += 32) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int u = 0; u < 32; u += 2) {
+          float x0, x1, e0, e1;
+          ffma2(x0, x1, sc[c0 + u], sc[c0 + u + 1], k2, k2, nmk, nmk);
+          if (((u >> 1) & 3) < kEmu / 2) {          // kEmu of every 8 exponentials on the FMA pipe
+            exp2_poly2(e0, e1, x0, x1);
+          } else {
+            e0 = ex2_approx(x0);
+            e1 = ex2_approx(x1);
+          }
+          fadd2(rs0, rs1, rs0, rs1, e0, e1);
+          pk[u >> 1] = pack_h2(e0, e1);
+        }
+        tmem_st_x16(prow + (c0 >> 1), pk);
+      }
+      tmem_st_wait();
+      l_run = l_run * alpha + (rs0 + rs1);
+      tc_fence_before();
+      mbar_arrive(smem_u32(&p_full[i]));
+    };
+    const int nfull = p.nkv / kKVTile;
+    for (int j = 0; j < nfull; ++j) block(j, std::false_type{});
+    if (nfull < nblk) block(nfull, std::true_type{});
+    mbar_wait(smem_u32(&pv_done[i]), (nblk - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.f / l_run;
+    const int qi = q0 + i * 128 + row;
+    __half* optr = p.out + (static_cast<long long>(b) * p.nq + qi) * p.ldo + head * DH;
+#pragma unroll
+    for (int c0 = 0; c0 < DH; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_x32(orow + c0, r);
+      tmem_ld_wait();
+      if (qi < p.nq) {
+#pragma unroll
+        for (int u = 0; u < 32; u += 8) {
+          uint4 v;
+          v.x = pack_h2(__uint_as_float(r[u]) * inv, __uint_as_float(r[u + 1]) * inv);
+          v.y = pack_h2(__uint_as_float(r[u + 2]) * inv, __uint_as_float(r[u + 3]) * inv);
+          v.z = pack_h2(__uint_as_float(r[u + 4]) * inv, __uint_as_float(r[u + 5]) * inv);
+          v.w = pack_h2(__uint_as_float(r[u + 6]) * inv, __uint_as_float(r[u + 7]) * inv);
+          *reinterpret_cast<uint4*>(optr + c0 + u) = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int attn_v3_emu() {   // exponentials per 8 evaluated on the FMA pipe: MGLD_ATTN_EMU = 0, 2 or 4
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MGLD_ATTN_EMU");
+    v = e ? atoi(e) : 2;
+    if (v != 0 && v != 2 && v != 4) v = 2;
+  }
+  return v;
+}
+
+static int launch_attention_v3(const mgld_attention_desc* d, cudaStream_t stream) {
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.nq = d->nq; p.nkv = d->nkv; p.heads = d->heads; p.batch = d->batch;
+  p.q_col0 = d->q_col0; p.k_col0 = d->k_col0; p.v_col0 = d->v_col0;
+  p.q_hstride = d->q_head_stride; p.k_hstride = d->k_head_stride; p.v_hstride = d->v_head_stride;
+  p.kv_batched = d->kv_batched;
+  p.scale_log2e = d->scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<__half*>(d->out); p.ldo = d->ldo;
+  CUtensorMap tmQ, tmK, tmV;
+  {
+    uint64_t dims[3] = {(uint64_t)d->ldq, (uint64_t)d->nq, (uint64_t)d->batch};
+    uint64_t str[2] = {(uint64_t)d->ldq * 2, (uint64_t)d->ldq * 2 * d->nq};
+    uint32_t box[3] = {64, 128, 1};
+    int rc = make_tmap_f16(&tmQ, d->q, 3, dims, str, box);
+    if (rc) return rc;
+    const int kvb = d->kv_batched ? d->batch : 1;
+    uint64_t dimsk[3] = {(uint64_t)d->ldk, (uint64_t)d->nkv, (uint64_t)kvb};
+    uint64_t strk[2] = {(uint64_t)d->ldk * 2, (uint64_t)d->ldk * 2 * d->nkv};
+    rc = make_tmap_f16(&tmK, d->k, 3, dimsk, strk, box);
+    if (rc) return rc;
+    uint64_t dimsv[3] = {(uint64_t)d->ldv, (uint64_t)d->nkv, (uint64_t)kvb};
+    uint64_t strv[2] = {(uint64_t)d->ldv * 2, (uint64_t)d->ldv * 2 * d->nkv};
+    rc = make_tmap_f16(&tmV, d->v, 3, dimsv, strv, box);
+    if (rc) return rc;
+  }
+  const int smem = 2 * 16384 + kV2Stages * 2 * 16384 + 1024;
+  using Fn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams);
+  static const Fn kFns[3] = {attention_v3_kernel<0>, attention_v3_kernel<2>, attention_v3_kernel<4>};
+  static bool attr_set = false;
+  if (!attr_set) {
+    for (int i = 0; i < 3; ++i) MGLD_CUDA(cudaFuncSetAttribute(kFns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(d->nq, 256), d->heads, d->batch);
+  kFns[attn_v3_emu() / 2]<<<grid, kV3Threads, smem, stream>>>(tmQ, tmK, tmV, p);
+  MGLD_LAUNCH_CHECK("attention_v3_kernel");
+  return MGLD_OK;
+}
+
 }  // namespace mgld
 
 using namespace mgld;
@@ -548,6 +886,8 @@ extern "C" int mgld_attention(const mgld_attention_desc* d, void* stream) {
   if (d->head_dim == 64) {
     // v2 (two query tiles per CTA, P in TMEM) pays off once there are >= 256 queries; MGLD_ATTN_V1=1 forces v1
     static const bool force_v1 = getenv("MGLD_ATTN_V1") != nullptr;
+    static const bool force_v2 = getenv("MGLD_ATTN_V2") != nullptr;
+    if (!force_v1 && !force_v2 && d->nq >= 256) return launch_attention_v3(d, (cudaStream_t)stream);
     if (!force_v1 && d->nq >= 256) return launch_attention_v2(d, (cudaStream_t)stream);
     return launch_attention<64>(d, (cudaStream_t)stream);
   }

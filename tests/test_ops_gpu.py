@@ -150,7 +150,8 @@ def test_geglu_and_spade_epilogues():
 
 
 @pytest.mark.parametrize("B,N,heads,dh,mode", [(1, 128, 1, 64, "self"), (5, 4096, 5, 64, "self"), (5, 1024, 10, 64, "self"),
-                                              (5, 64, 20, 64, "self"), (2, 200, 3, 64, "self"), (5, 4096, 5, 64, "cross"),
+                                              (5, 64, 20, 64, "self"), (2, 200, 3, 64, "self"), (2, 300, 3, 64, "self"),
+                                              (1, 520, 2, 64, "self"), (5, 4096, 5, 64, "cross"),
                                               (5, 64, 20, 64, "cross"), (5, 4096, 4, 64, "legacy"), (5, 256, 4, 128, "legacy"),
                                               (5, 64, 4, 128, "legacy")])
 def test_attention(B, N, heads, dh, mode):
