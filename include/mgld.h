@@ -120,6 +120,9 @@ typedef struct mgld_attention_desc {
 } mgld_attention_desc;
 
 int mgld_attention(const mgld_attention_desc* d, void* stream);
+/* Development hook: per-CTA cycle counters ([CTAs][16] int64, device memory) filled by the following head-dim-64 attention
+   launches (which role waits for which); null switches it off (the default). */
+void mgld_attention_set_debug_counters(void* dev_ptr);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Flow-guided latent ops (fp32, NCHW: the layout the reference keeps latents / flows in)

@@ -37,6 +37,8 @@ struct AttnParams {
   float scale_log2e;                 // scale * log2(e)
   __half* out;
   int ldo;                           // out row pitch (elements); out[(b*nq + i)*ldo + h*DH + d]
+  int seq;                           // v3: the two softmax warpgroups take turns on the exponential section
+  long long* dbg;                    // optional per-CTA cycle counters [CTAs][16] (mgld_attention_set_debug_counters); null in production
 };
 
 template <int DH>
@@ -555,23 +557,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// d = a * b + c on two fp32 lanes at once (sm_100 packed fp32)
-__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
-  asm("{\n.reg .b64 ra, rb, rc, rd;\n"
-      "mov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmov.b64 rc, {%6, %7};\n"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n"
-      "mov.b64 {%0, %1}, rd;\n}"
-      : "=f"(d0), "=f"(d1)
-      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
-}
-__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
-  asm("{\n.reg .b64 ra, rb, rd;\n"
-      "mov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\n"
-      "add.rn.f32x2 rd, ra, rb;\n"
-      "mov.b64 {%0, %1}, rd;\n}"
-      : "=f"(d0), "=f"(d1)
-      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
-}
 // 2^x for x in [-125, 125] on the FMA / ALU pipes: n = round(x) via the 1.5 * 2^23 trick, 2^(x - n) by a degree-3 minimax
 // polynomial on [-0.5, 0.5], exponent patched in with an integer add.  Two lanes at a time.
 __device__ __forceinline__ void exp2_poly2(float& y0, float& y1, float x0, float x1) {
@@ -596,7 +581,7 @@ __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.
 template <int N>
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
-template <int kEmu>
+template <int kEmu, bool kDbg>
 __global__ void __launch_bounds__(kV3Threads, 1)
 attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -606,7 +591,7 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t q_full, kv_full[kV2Stages], kv_empty[kV2Stages], s_full[2], s_free[2], p_full[2],
-      pv_done[2];
+      pv_done[2], exp_turn[2];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -625,9 +610,10 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int s = 0; s < kV2Stages; ++s) { mbar_init(smem_u32(&kv_full[s]), 1); mbar_init(smem_u32(&kv_empty[s]), 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&s_full[i]), 1);
-      mbar_init(smem_u32(&s_free[i]), 128);
-      mbar_init(smem_u32(&p_full[i]), 128);
+      mbar_init(smem_u32(&s_free[i]), 4);     // one arrival per softmax warp (lane 0, after __syncwarp): 128 lanes
+      mbar_init(smem_u32(&p_full[i]), 4);     // arriving on one barrier word serialise in the shared-memory atomic unit
       mbar_init(smem_u32(&pv_done[i]), 1);
+      mbar_init(smem_u32(&exp_turn[i]), 4);
     }
     fence_mbar_init();
   }
@@ -636,6 +622,19 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  // kDbg = false folds every `if (dbg)` below away (the production instantiations)
+  long long* const dbg = (kDbg && p.dbg) ? p.dbg + 16 * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
+  const long long dbg_t0 = dbg ? clock64() : 0;
+  // wait on a barrier, adding the cycles spent to `acc` when the development counters are on
+  auto wait_t = [&](uint32_t bar, uint32_t parity, long long& acc) {
+    if (dbg) {
+      const long long t = clock64();
+      mbar_wait_poll(bar, parity);
+      acc += clock64() - t;
+    } else {
+      mbar_wait_poll(bar, parity);
+    }
+  };
 
   if (warp < 4) {
   setmaxnreg_dec<88>();
@@ -644,56 +643,84 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_expect_tx(smem_u32(&q_full), 2 * kTileBytes);
       tma_load_3d(sQ, &tmQ, smem_u32(&q_full), p.q_col0 + head * p.q_hstride, q0, b);
       tma_load_3d(sQ + kTileBytes, &tmQ, smem_u32(&q_full), p.q_col0 + head * p.q_hstride, q0 + 128, b);
+      long long w_empty = 0;
       for (int j = 0; j < nblk; ++j) {
         const int s = j % kV2Stages;
-        mbar_wait(smem_u32(&kv_empty[s]), ((j / kV2Stages) & 1) ^ 1);
+        mbar_wait(smem_u32(&kv_empty[s]), ((j / kV2Stages) & 1) ^ 1);   // parked by the hardware, not polling
+        (void)w_empty;
         const uint32_t fb = smem_u32(&kv_full[s]);
         mbar_expect_tx(fb, 2 * kTileBytes);
         tma_load_3d(sKV + s * 2 * kTileBytes, &tmK, fb, p.k_col0 + head * p.k_hstride, j * kKVTile, kvb);
         tma_load_3d(sKV + s * 2 * kTileBytes + kTileBytes, &tmV, fb, p.v_col0 + head * p.v_hstride, j * kKVTile, kvb);
       }
+      if (dbg) dbg[14] = w_empty;
     }
   } else if (warp == 1) {
-    if (elect_one()) {
+    {
+      // Issue loop.  All 32 lanes run the loop and the waits; only the tcgen05 instructions are predicated on the elected
+      // lane.  That keeps the loop state (descriptors, stage, barrier phases) warp-uniform, so it lives in uniform
+      // registers and feeds UTCHMMA directly instead of going through a scalar chain of 64-bit adds + R2UR per operand
+      // (this chain competes with two softmax warps for the scheduler; it set the latency from "P is ready" to "PV is
+      // issued").  All state is carried incrementally; descriptors are base + compile-time offset (the 14-bit address
+      // field never carries into the next field).
+      const bool leader = elect_one();
       const uint32_t idesc_s = umma_idesc_f16(128, kKVTile, 0, 0);
       const uint32_t idesc_o = umma_idesc_f16(128, DH, 0, 1);  // B = V, MN-major
-      auto issue_s = [&](int i, int j) {
-        const uint32_t sk = sKV + (j % kV2Stages) * 2 * kTileBytes;
-        const uint32_t sq = sQ + i * kTileBytes;
+      const uint64_t dq = umma_smem_desc(sQ, 0, 1024, kSwz128);
+      const uint64_t dkv0 = umma_smem_desc(sKV, 0, 1024, kSwz128);
+      constexpr uint32_t kStageStep = (2 * kTileBytes) >> 4;
+      const uint32_t bar_sfull = smem_u32(&s_full[0]), bar_sfree = smem_u32(&s_free[0]), bar_pfull = smem_u32(&p_full[0]);
+      const uint32_t bar_pvdone = smem_u32(&pv_done[0]), bar_kvfull = smem_u32(&kv_full[0]), bar_kvempty = smem_u32(&kv_empty[0]);
+      const uint32_t ts = tmem_base + kSCol, tp = tmem_base + kPCol, to = tmem_base + kOCol;
+      auto issue_s = [&](const int i, const uint64_t dk) {
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k)
-          umma_ss(tmem_base + kSCol + i * 128, umma_smem_desc(sq + k * 32, 0, 1024, kSwz128),
-                  umma_smem_desc(sk + k * 32, 0, 1024, kSwz128), idesc_s, k != 0);
-        umma_commit(smem_u32(&s_full[i]));
+          for (int k = 0; k < DH / 16; ++k)
+            umma_ss(ts + i * 128, dq + ((i * kTileBytes + k * 32) >> 4), dk + ((k * 32) >> 4), idesc_s, k != 0);
+          umma_commit(bar_sfull + 8 * i);
+        }
       };
-      mbar_wait(smem_u32(&q_full), 0);
-      mbar_wait(smem_u32(&kv_full[0]), 0);
+      mbar_wait_poll(smem_u32(&q_full), 0);
+      mbar_wait_poll(bar_kvfull, 0);
       tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
+      issue_s(0, dkv0);
+      issue_s(1, dkv0);
+      int st = 0, st_next = 1;                   // stage of block j / j + 1
+      uint32_t ph_next = 0;                      // kv_full parity of block j + 1
+      uint64_t dkv = dkv0;                       // K descriptor of block j (V = + kTileBytes)
+      uint64_t dkv_next = dkv0 + kStageStep;
+      uint32_t par = 0;                          // j & 1
+      long long w_kv = 0, w_sfree = 0, w_pfull = 0;
+      const long long t_loop = dbg ? clock64() : 0;
       for (int j = 0; j < nblk; ++j) {
-        const int s = j % kV2Stages;
-        const uint32_t sv = sKV + s * 2 * kTileBytes + kTileBytes;
         if (j + 1 < nblk) {
-          mbar_wait(smem_u32(&kv_full[(j + 1) % kV2Stages]), ((j + 1) / kV2Stages) & 1);   // K_{j+1} has landed
+          wait_t(bar_kvfull + 8 * st_next, ph_next, w_kv);   // K_{j+1} has landed
+#pragma unroll
           for (int i = 0; i < 2; ++i) {
-            mbar_wait(smem_u32(&s_free[i]), j & 1);   // softmax_i holds S_i(j) in registers: the buffer is free
+            wait_t(bar_sfree + 8 * i, par, w_sfree);      // softmax_i holds S_i(j) in registers: the buffer is free
             tc_fence_after();
-            issue_s(i, j + 1);
+            issue_s(i, dkv_next);
           }
         }
-        for (int i = 0; i < 2; ++i) {
-          mbar_wait(smem_u32(&p_full[i]), j & 1);
-          tc_fence_after();
-          const uint32_t pcol = tmem_base + kPCol + i * 64;
-          const uint32_t ocol = tmem_base + kOCol + i * 64;
+        const uint64_t dv = dkv + (kTileBytes >> 4);
 #pragma unroll
-          for (int k = 0; k < kKVTile / 16; ++k)  // A: 16 keys = 8 packed columns per step; B: 16 key rows = 2048 B
-            umma_ts(ocol, pcol + k * 8, umma_smem_desc(sv + k * 2048, 0, 1024, kSwz128), idesc_o, (j | k) != 0);
-          umma_commit(smem_u32(&pv_done[i]));
-          if (i == 1) umma_commit(smem_u32(&kv_empty[s]));
+        for (int i = 0; i < 2; ++i) {
+          wait_t(bar_pfull + 8 * i, par, w_pfull);
+          tc_fence_after();
+          if (leader) {
+#pragma unroll
+            for (int k = 0; k < kKVTile / 16; ++k)  // A: 16 keys = 8 packed columns per step; B: 16 key rows = 2048 B
+              umma_ts(to + i * 64, tp + i * 64 + k * 8, dv + ((k * 2048) >> 4), idesc_o, (j | k) != 0);
+            umma_commit(bar_pvdone + 8 * i);
+            if (i == 1) umma_commit(bar_kvempty + 8 * st);
+          }
         }
+        par ^= 1;
+        st = st_next;
+        dkv = dkv_next;
+        if (++st_next == kV2Stages) { st_next = 0; ph_next ^= 1; dkv_next = dkv0; } else { dkv_next += kStageStep; }
       }
+      if (dbg && leader) { dbg[0] = w_kv; dbg[1] = w_sfree; dbg[2] = w_pfull; dbg[3] = clock64() - t_loop; }
     }
   }
   } else {
@@ -708,18 +735,27 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t orow = tmem_base + lane_off + kOCol + i * 64;
     const float k2 = p.scale_log2e;
     float m_run = -INFINITY, l_run = 0.f;
-    // one 128-key block of this thread's query row.  kMasked: the last, partial block (keys beyond nkv are masked);
-    // a separate instantiation so that the full blocks carry no per-element select
-    auto block = [&](const int j, auto masked_tag) {
-      constexpr bool kMasked = decltype(masked_tag)::value;
-      mbar_wait(smem_u32(&s_full[i]), j & 1);
+    long long w_sfull = 0, w_pv = 0, w_seq = 0, c_exp = 0;
+    const long long t_loop = dbg ? clock64() : 0;
+    // The score row of the current block lives in registers.  Its load for block j+1 is issued as soon as the
+    // exponentials of block j are done, so the S wait and the TMEM load latency hide behind the wait for the P store.
+    float sc[kKVTile];
+    auto load_scores = [&](const int j) {
+      wait_t(smem_u32(&s_full[i]), j & 1, w_sfull);
       tc_fence_after();
-      float sc[kKVTile];
 #pragma unroll
       for (int c0 = 0; c0 < kKVTile; c0 += 32) tmem_ld_x32(srow + c0, reinterpret_cast<uint32_t*>(sc) + c0);
+    };
+    auto scores_loaded = [&]() {   // S_i is in registers: hand the buffer back for S_i(j+1)
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(smem_u32(&s_free[i]));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_free[i]));
+    };
+    // one 128-key block of this thread's query row.  kMasked: the last, partial block (keys beyond nkv are masked);
+    // a separate instantiation so that the full blocks carry no per-element select
+    auto block = [&](const int j, auto masked_tag, const bool has_next) {
+      constexpr bool kMasked = decltype(masked_tag)::value;
       if constexpr (kMasked) {
         const int kv_left = p.nkv - j * kKVTile;
 #pragma unroll
@@ -745,24 +781,9 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         m_run = mx;
       }
       const float nmk = -m_run * k2;
-      if (j > 0) {
-        // PV_i(j-1) has consumed P_i and O_i is quiescent.  It was issued a full softmax block ago: this wait is free in
-        // steady state, and taking it here lets every 32-column chunk of P go to TMEM as soon as it is computed.
-        mbar_wait(smem_u32(&pv_done[i]), (j - 1) & 1);
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, grow)) {
-#pragma unroll
-          for (int c0 = 0; c0 < DH; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld_x32(orow + c0, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int u = 0; u < 32; ++u) r[u] = __float_as_uint(__uint_as_float(r[u]) * alpha);
-            tmem_st_x32(orow + c0, r);
-          }
-        }
-      }
+      if (p.seq && (i == 1 || j > 0)) wait_t(smem_u32(&exp_turn[i ^ 1]), (i == 1 ? j : j - 1) & 1, w_seq);
       float rs0 = 0.f, rs1 = 0.f;
+      const long long t_exp = dbg ? clock64() : 0;
 #pragma unroll
       for (int c0 = 0; c0 < kKVTile; c0 += 32) {
         uint32_t pk[16];
@@ -779,17 +800,45 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           fadd2(rs0, rs1, rs0, rs1, e0, e1);
           pk[u >> 1] = pack_h2(e0, e1);
         }
+        if (c0 == 0 && j > 0) {
+          // P_i may only be overwritten (and O_i rescaled) once PV_i(j-1) is complete.  The wait sits behind the first
+          // chunk of exponentials: by then the PV issued at the end of the previous block has long finished.
+          wait_t(smem_u32(&pv_done[i]), (j - 1) & 1, w_pv);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll
+            for (int o0 = 0; o0 < DH; o0 += 16) {
+              uint32_t r[16];
+              tmem_ld_x16(orow + o0, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int u = 0; u < 16; ++u) r[u] = __float_as_uint(__uint_as_float(r[u]) * alpha);
+              tmem_st_x16(orow + o0, r);
+            }
+          }
+        }
         tmem_st_x16(prow + (c0 >> 1), pk);
       }
+      if (p.seq) { __syncwarp(); if (lane == 0) mbar_arrive(smem_u32(&exp_turn[i])); }
+      if (dbg) c_exp += clock64() - t_exp;
+      if (has_next) load_scores(j + 1);
       tmem_st_wait();
       l_run = l_run * alpha + (rs0 + rs1);
       tc_fence_before();
-      mbar_arrive(smem_u32(&p_full[i]));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&p_full[i]));
+      if (has_next) scores_loaded();
     };
     const int nfull = p.nkv / kKVTile;
-    for (int j = 0; j < nfull; ++j) block(j, std::false_type{});
-    if (nfull < nblk) block(nfull, std::true_type{});
-    mbar_wait(smem_u32(&pv_done[i]), (nblk - 1) & 1);
+    load_scores(0);
+    scores_loaded();
+    for (int j = 0; j < nfull; ++j) block(j, std::false_type{}, j + 1 < nblk);
+    if (nfull < nblk) block(nfull, std::true_type{}, false);
+    if (dbg && (threadIdx.x & 127) == 0) {
+      long long* d = dbg + 4 + 5 * i;
+      d[0] = w_sfull; d[1] = w_pv; d[2] = w_seq; d[3] = c_exp; d[4] = clock64() - t_loop;
+    }
+    mbar_wait_poll(smem_u32(&pv_done[i]), (nblk - 1) & 1);
     tc_fence_after();
     const float inv = 1.f / l_run;
     const int qi = q0 + i * 128 + row;
@@ -814,11 +863,14 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[15] = clock64() - dbg_t0;
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
 }
+
+static long long* g_attn_dbg = nullptr;
 
 static int attn_v3_emu() {   // exponentials per 8 evaluated on the FMA pipe: MGLD_ATTN_EMU = 0, 2 or 4
   static int v = -1;
@@ -839,6 +891,12 @@ static int launch_attention_v3(const mgld_attention_desc* d, cudaStream_t stream
   p.kv_batched = d->kv_batched;
   p.scale_log2e = d->scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__half*>(d->out); p.ldo = d->ldo;
+  p.dbg = g_attn_dbg;
+  {
+    static int seq = -1;
+    if (seq < 0) { const char* e = getenv("MGLD_ATTN_SEQ"); seq = e ? (atoi(e) != 0) : 0; }   // off: measured slower (profiles/r01_dev_run21*)
+    p.seq = seq;
+  }
   CUtensorMap tmQ, tmK, tmV;
   {
     uint64_t dims[3] = {(uint64_t)d->ldq, (uint64_t)d->nq, (uint64_t)d->batch};
@@ -858,14 +916,15 @@ static int launch_attention_v3(const mgld_attention_desc* d, cudaStream_t stream
   }
   const int smem = 2 * 16384 + kV2Stages * 2 * 16384 + 1024;
   using Fn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams);
-  static const Fn kFns[3] = {attention_v3_kernel<0>, attention_v3_kernel<2>, attention_v3_kernel<4>};
+  static const Fn kFns[4] = {attention_v3_kernel<0, false>, attention_v3_kernel<2, false>, attention_v3_kernel<4, false>,
+                             attention_v3_kernel<2, true>};
   static bool attr_set = false;
   if (!attr_set) {
-    for (int i = 0; i < 3; ++i) MGLD_CUDA(cudaFuncSetAttribute(kFns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int i = 0; i < 4; ++i) MGLD_CUDA(cudaFuncSetAttribute(kFns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   dim3 grid(ceil_div(d->nq, 256), d->heads, d->batch);
-  kFns[attn_v3_emu() / 2]<<<grid, kV3Threads, smem, stream>>>(tmQ, tmK, tmV, p);
+  kFns[p.dbg ? 3 : attn_v3_emu() / 2]<<<grid, kV3Threads, smem, stream>>>(tmQ, tmK, tmV, p);
   MGLD_LAUNCH_CHECK("attention_v3_kernel");
   return MGLD_OK;
 }
@@ -873,6 +932,11 @@ static int launch_attention_v3(const mgld_attention_desc* d, cudaStream_t stream
 }  // namespace mgld
 
 using namespace mgld;
+
+// Development hook: per-CTA cycle counters of the next attention (v3) launches ([CTAs][16] int64, device memory):
+// 0-3 MMA thread (wait kv_full, wait s_free, wait p_full, loop total); 4-8 / 9-13 softmax warpgroup 0 / 1 (wait s_full,
+// wait pv_done, wait for the exponential turn, exponentials + P store issue, loop total); 14 TMA wait kv_empty; 15 kernel total.
+extern "C" void mgld_attention_set_debug_counters(void* dev_ptr) { g_attn_dbg = reinterpret_cast<long long*>(dev_ptr); }
 
 extern "C" int mgld_attention(const mgld_attention_desc* d, void* stream) {
   if (!initialised()) { set_error("mgld_init() has not been called"); return MGLD_ERR_NOT_INIT; }

@@ -65,7 +65,7 @@ __device__ __forceinline__ void act_inplace32(float* v, int act) {
       break;
     case MGLD_ACT_SILU:
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = v[i] / (1.f + __expf(-v[i]));
+      for (int i = 0; i < 32; ++i) v[i] = __fdividef(v[i], 1.f + __expf(-v[i]));
       break;
     case MGLD_ACT_LRELU02:
 #pragma unroll
@@ -73,7 +73,7 @@ __device__ __forceinline__ void act_inplace32(float* v, int act) {
       break;
     case MGLD_ACT_GELU:
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
+      for (int i = 0; i < 32; i += 2) gelu_poly2(v[i], v[i + 1], v[i], v[i + 1]);
       break;
     case MGLD_ACT_SIGMOID:
 #pragma unroll
@@ -497,9 +497,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 32; ++i) { v[i] += bias_s[c0 + i]; g[i] += bias_s[64 + c0 + i]; }
-              act_inplace32(g, MGLD_ACT_GELU);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] *= g[i];
+              for (int i = 0; i < 32; i += 2) {   // value * gelu(gate)
+                float g0, g1;
+                gelu_poly2(g0, g1, g[i], g[i + 1]);
+                v[i] *= g0;
+                v[i + 1] *= g1;
+              }
               if (has_res) {
                 float r[32];
                 load_stage32(staging, row, c0, r, p.panel_cols);

@@ -113,26 +113,45 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, int ld1, 
   extern __shared__ float sh[];  // [2*G] mean, rstd
   const int C = C1 + C2, vpr = C >> 3, cpg = C / G;
   const int t = blockIdx.y;
-  const double count = (double)HW * cpg;
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    const double mean = sums[(static_cast<long long>(t) * G + g) * 2] / count;
-    double var = sums[(static_cast<long long>(t) * G + g) * 2 + 1] / count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    sh[2 * g] = (float)mean;
-    sh[2 * g + 1] = (float)(1.0 / sqrt(var + eps));
-  }
-  __syncthreads();
-  // each block covers kGnApplyItems consecutive 8-channel vectors of frame t; 4 independent loads in flight per thread
-  const long long base = static_cast<long long>(blockIdx.x) * kGnApplyItems;
+  // each block covers kGnApplyItems consecutive 8-channel vectors of frame t.  All of a thread's loads are issued before
+  // the first one is consumed (an early `break` on the bounds check inside the unrolled loop used to serialise them: one
+  // 16-byte load in flight per thread, ~2.5 TB/s on L2-resident maps).
+  // A block owns a contiguous range of the frame's vectors; the launcher sizes the ranges so that the whole grid is
+  // resident at once (1600 blocks on 1184 slots ran as two waves, the second one a third full).
   const long long total = static_cast<long long>(HW) * vpr;
+  const long long per = (total + gridDim.x - 1) / gridDim.x;
+  const long long base0 = static_cast<long long>(blockIdx.x) * per;
+  const long long end = base0 + per < total ? base0 + per : total;
+  constexpr int kPer = kGnApplyItems / 256;
+  for (long long base = base0; base < end; base += kGnApplyItems) {
+  uint4 u[kPer];
+  int rr[kPer], vv[kPer];
 #pragma unroll
-  for (int j = 0; j < kGnApplyItems / 256; ++j) {
+  for (int j = 0; j < kPer; ++j) {
     const long long idx = base + j * 256 + threadIdx.x;
-    if (idx >= total) break;
-    const int r = idx / vpr, v = idx - static_cast<long long>(r) * vpr;
-    const long long m = static_cast<long long>(t) * HW + r;
+    const bool live = idx < end;
+    rr[j] = live ? static_cast<int>(idx / vpr) : -1;
+    vv[j] = live ? static_cast<int>(idx - static_cast<long long>(rr[j]) * vpr) : 0;
+    u[j] = live ? load_cat8(x1, C1, ld1, x2, ld2, static_cast<long long>(t) * HW + rr[j], vv[j] * 8) : make_uint4(0, 0, 0, 0);
+  }
+  if (base == base0) {   // (mean, rstd) of the frame's groups, while the first loads are in flight
+    const double count = (double)HW * cpg;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+      const double mean = sums[(static_cast<long long>(t) * G + g) * 2] / count;
+      double var = sums[(static_cast<long long>(t) * G + g) * 2 + 1] / count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      sh[2 * g] = (float)mean;
+      sh[2 * g + 1] = (float)(1.0 / sqrt(var + eps));
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    if (rr[j] < 0) continue;
+    const int v = vv[j];
+    const long long m = static_cast<long long>(t) * HW + rr[j];
     float f[8];
-    unpack8(load_cat8(x1, C1, ld1, x2, ld2, m, v * 8), f);
+    unpack8(u[j], f);
     float gm[8], bt[8];
     if (gamma) {
       const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), gb = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
@@ -155,10 +174,11 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, int ld1, 
     for (int i = 0; i < 8; ++i) {
       float y = f[i];
       if (gamma) y = fmaf(y, gm[i], bt[i]);
-      if (silu) y = y / (1.f + __expf(-y));
+      if (silu) y = __fdividef(y, 1.f + __expf(-y));   // MUFU.RCP + FMUL instead of the ~8-instruction IEEE division
       f[i] = y;
     }
     *reinterpret_cast<uint4*>(out + m * ldo + v * 8) = pack8(f);
+  }
   }
 }
 
@@ -297,7 +317,7 @@ __global__ void __launch_bounds__(kGnFusedThreads, 1) gn_fused_kernel(const GnFu
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float y = fmaf(f[i], sc[i], sh[i]);
-        if (p.silu) y = y / (1.f + __expf(-y));
+        if (p.silu) y = __fdividef(y, 1.f + __expf(-y));
         f[i] = y;
       }
       *reinterpret_cast<uint4*>(p.out + (m0 + r) * p.ldo + c0) = pack8(f);
@@ -305,17 +325,21 @@ __global__ void __launch_bounds__(kGnFusedThreads, 1) gn_fused_kernel(const GnFu
   }
 }
 
-// LayerNorm over the last dim, one warp per row (C <= 2048, multiple of 8)
+// LayerNorm over the last dim, one warp per row (C <= 2048, multiple of 8).  kVec = 16-byte vectors per lane, compile
+// time: the row lives in kVec * 8 registers (C = 320 needs 2, not the generic 8), which is what lets enough warps be
+// resident to cover the load -> reduce -> reduce -> store latency chain of each row.
 constexpr int kLnMaxVec = 8;  // vectors of 8 per lane
-__global__ void layernorm_kernel(const __half* __restrict__ x, int ldx, int M, int C, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, float eps, __half* __restrict__ out, int ldo) {
+template <int kVec>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __half* __restrict__ x, int ldx, int M, int C, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, __half* __restrict__ out, int ldo) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= M) return;
   const int vpr = C >> 3;
-  float f[kLnMaxVec][8];
+  float f[kVec][8];
   float s = 0.f;
 #pragma unroll
-  for (int k = 0; k < kLnMaxVec; ++k) {
+  for (int k = 0; k < kVec; ++k) {
     const int v = lane + 32 * k;
     if (v < vpr) {
       unpack8(__ldg(reinterpret_cast<const uint4*>(x + static_cast<long long>(warp) * ldx + v * 8)), f[k]);
@@ -327,7 +351,7 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, int ldx, int M, i
   const float mean = s / (float)C;
   float q = 0.f;
 #pragma unroll
-  for (int k = 0; k < kLnMaxVec; ++k) {
+  for (int k = 0; k < kVec; ++k) {
     if (lane + 32 * k < vpr) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) { const float d = f[k][i] - mean; q = fmaf(d, d, q); }
@@ -336,7 +360,7 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, int ldx, int M, i
   for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q / (float)C + eps);
 #pragma unroll
-  for (int k = 0; k < kLnMaxVec; ++k) {
+  for (int k = 0; k < kVec; ++k) {
     const int v = lane + 32 * k;
     if (v < vpr) {
       float y[8];
@@ -417,7 +441,16 @@ extern "C" int mgld_gn_apply_f16(const void* x1, int C1, int ld1, const void* x2
   MGLD_CHECK_ARG(x1 && sums && out && T > 0 && HW > 0 && groups > 0, "gn_apply: bad arguments");
   MGLD_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0 && C % groups == 0, "gn_apply: C1=%d C2=%d G=%d", C1, C2, groups);
   MGLD_CHECK_ARG((gamma != nullptr) == (beta != nullptr), "gn_apply: gamma/beta");
-  dim3 grid((unsigned)((static_cast<long long>(HW) * (C / 8) + kGnApplyItems - 1) / kGnApplyItems), T);
+  long long bx = (static_cast<long long>(HW) * (C / 8) + kGnApplyItems - 1) / kGnApplyItems;
+  static int occ = -1;   // resident blocks per SM (register-limited)
+  if (occ < 0) {
+    int n = 0;
+    MGLD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gn_apply_kernel, 256, 2 * groups * sizeof(float)));
+    occ = n > 0 ? n : 1;
+  }
+  const long long resident = static_cast<long long>(num_sms()) * occ / T;   // one wave: T frames share the machine
+  if (bx > resident && resident >= 1) bx = resident;
+  dim3 grid((unsigned)bx, T);
   gn_apply_kernel<<<grid, 256, 2 * groups * sizeof(float), (cudaStream_t)stream>>>(
       (const __half*)x1, C1, ld1 > 0 ? ld1 : C1, (const __half*)x2, C2, ld2 > 0 ? ld2 : C2, HW, groups, sums, eps,
       gamma, beta, silu, (__half*)out, ldo > 0 ? ldo : C);
@@ -503,8 +536,19 @@ extern "C" int mgld_layernorm_f16(const void* x, int ldx, int M, int C, const fl
   MGLD_CHECK_ARG(x && out && gamma && beta && M > 0, "layernorm: bad arguments");
   MGLD_CHECK_ARG(C % 8 == 0 && C / 8 <= 32 * kLnMaxVec, "layernorm: C=%d unsupported", C);
   const int warps_per_block = 8;
-  layernorm_kernel<<<ceil_div(M, warps_per_block), warps_per_block * 32, 0, (cudaStream_t)stream>>>(
-      (const __half*)x, ldx > 0 ? ldx : C, M, C, gamma, beta, eps, (__half*)out, ldo > 0 ? ldo : C);
+  const int vec = ceil_div(C / 8, 32);
+  const dim3 grid(ceil_div(M, warps_per_block)), block(warps_per_block * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  const __half* xp = (const __half*)x;
+  __half* op = (__half*)out;
+  const int lx = ldx > 0 ? ldx : C, lo = ldo > 0 ? ldo : C;
+  switch (vec) {
+    case 1: layernorm_kernel<1><<<grid, block, 0, st>>>(xp, lx, M, C, gamma, beta, eps, op, lo); break;
+    case 2: layernorm_kernel<2><<<grid, block, 0, st>>>(xp, lx, M, C, gamma, beta, eps, op, lo); break;
+    case 3: layernorm_kernel<3><<<grid, block, 0, st>>>(xp, lx, M, C, gamma, beta, eps, op, lo); break;
+    case 4: case 5: layernorm_kernel<5><<<grid, block, 0, st>>>(xp, lx, M, C, gamma, beta, eps, op, lo); break;
+    default: layernorm_kernel<kLnMaxVec><<<grid, block, 0, st>>>(xp, lx, M, C, gamma, beta, eps, op, lo); break;
+  }
   MGLD_LAUNCH_CHECK("layernorm_kernel");
   return MGLD_OK;
 }

@@ -8,7 +8,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmgld.so")
+LIB_PATH = os.environ.get("MGLD_LIB") or os.path.join(_HERE, "libmgld.so")   # MGLD_LIB: development A/B builds only
 
 _lib = None
 _inited = set()

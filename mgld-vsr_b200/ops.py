@@ -3,6 +3,7 @@
 These wrappers only marshal pointers/sizes into the C structs; all arithmetic happens in libmgld.so.
 """
 import ctypes
+import os
 
 import torch
 
@@ -432,11 +433,31 @@ def conv_small_f32(x, w, bias):
     return out
 
 
+# conv3x3 with <= 8 output channels (UNet / VAE heads).  A 3x3 conv over C >= 64 channels is long-K GEMM work even when
+# only 3-4 output channels are wanted: padding the filter bank to a 32-row tile and running it on the tensor cores (7/8 of
+# the MMA columns are zeros) is ~10x faster than the CUDA-core kernel (warp per pixel, 168 us for the UNet head at 10x64x64,
+# 2 ms for the VAE head at 5x512x512).  MGLD_SMALL_COUT_GEMM=0 keeps the CUDA-core kernel.
+SMALL_COUT_GEMM = os.environ.get("MGLD_SMALL_COUT_GEMM", "1") != "0"
+_SMALL_COUT_PAD = {}
+
+
 def conv3x3_small_cout(x, w_packed, bias):
     """x NHWC fp16 [N,H,W,C], w_packed fp16 [Cout, 9*C] -> (N,Cout,H,W) fp32"""
     assert x.dtype == torch.float16 and x.is_contiguous()
     n, h, wd, c = x.shape
     cout = w_packed.shape[0]
+    if SMALL_COUT_GEMM and c % 64 == 0 and cout <= 32:
+        key = (w_packed.data_ptr(), bias.data_ptr() if bias is not None else 0)
+        ent = _SMALL_COUT_PAD.get(key)
+        if ent is None:
+            wp = torch.zeros(32, w_packed.shape[1], device=x.device, dtype=torch.float16)
+            wp[:cout] = w_packed
+            bp = torch.zeros(32, device=x.device, dtype=torch.float32)
+            if bias is not None:
+                bp[:cout] = bias
+            ent = _SMALL_COUT_PAD[key] = (wp, bp, w_packed, bias)     # the originals are kept alive: the key is their address
+        y = conv_gemm(x, ent[0], taps=TAPS_3X3, bias=ent[1], out_f32=True, block_n=32)      # [N,H,W,32] fp32
+        return y[..., :cout].permute(0, 3, 1, 2).contiguous()
     out = torch.empty(n, cout, h, wd, device=x.device, dtype=torch.float32)
     _count(1)
     _L.check(_L.lib().mgld_conv3x3_small_cout_f16(_L.ptr(x), _L.ptr(w_packed), _L.ptr(bias), _L.ptr(out), n, h, wd, c,

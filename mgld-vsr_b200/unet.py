@@ -115,7 +115,7 @@ def _gn_silu(ops, x, gb, eps, silu=True, x2=None):
 class _ResBlock:
     """ResBlock (openaimodel.py:233-360) and ResBlockDual (:362-482).  `dual` adds the SPADE tail."""
 
-    def __init__(self, P, p, cin, cout, dual, emb_slices):
+    def __init__(self, P, p, cin, cout, dual, emb_slices, spade_shared=None, level=0):
         self.cin, self.cout, self.dual = cin, cout, dual
         self.n1 = P.norm(p + ".in_layers.0")
         self.w1, b1 = P.conv(p + ".in_layers.2")
@@ -128,11 +128,14 @@ class _ResBlock:
             s = p + ".spade"
             self.sn = P.norm(s + ".param_free_norm")
             self.ws, self.bs = P.conv(s + ".mlp_shared.0")
+            self.sp_level, self.sp_slot = level, (spade_shared.add(level, self.ws, self.bs) if spade_shared is not None
+                                                  else None)
             wg, bg = P.conv(s + ".mlp_gamma")
             wb, bb = P.conv(s + ".mlp_beta")
             self.wgb, self.bgb = interleave_pair(wg, wb), interleave_pair(bg, bb)
 
-    def __call__(self, ops, x, emb_bias, seg=None, x2=None, pool=None):
+    def __call__(self, ops, x, emb_bias, seg=None, x2=None, pool=None, actv=None):
+        """seg: the struct-cond map of this resolution; actv: ReLU(mlp_shared(seg)) if the owner already computed it"""
         a1 = _gn_silu(ops, x, self.n1, 1e-5, True, x2)
         s1 = pool.next() if pool is not None else None
         h = _tag(ops.conv_gemm(a1, self.w1, taps=TAPS_3X3, bias=emb_bias[self.emb_idx], stats_out=s1), s1)
@@ -150,7 +153,8 @@ class _ResBlock:
         T, H, W, C = h2.shape
         st = ops.gn_finalize(s2, H * W, C, 1e-5) if s2 is not None else \
             ops.group_norm(h2, None, None, 1e-5, False, want_out=False, want_stats=True)
-        actv = ops.conv_gemm(seg, self.ws, taps=TAPS_3X3, bias=self.bs, act=ACT_RELU)
+        if actv is None:
+            actv = ops.conv_gemm(seg, self.ws, taps=TAPS_3X3, bias=self.bs, act=ACT_RELU)
         return _tag(ops.conv_gemm(actv, self.wgb, taps=TAPS_3X3, bias=self.bgb, epilogue=EPI_SPADE, h=h2, gn_stats=st,
                                   gn_weight=self.sn[0], gn_bias=self.sn[1], groups=32, res=sk, beta=1.0, stats_out=so), so)
 
@@ -175,6 +179,35 @@ class _EmbSlices:
     def run(self, ops, emb):
         y = ops.gemv(emb, self.w, bias=self.b, silu_in=True)
         return [y[self.off[i]:self.off[i + 1]] for i in range(len(self.off) - 1)]
+
+
+class _SpadeShared:
+    """SPADE's first conv, ReLU(conv3x3(segmap 256 -> 128)) (spade.py:83-85), only depends on the struct-cond map of its
+    resolution, not on the UNet activations: the 5-7 ResBlocks of one resolution level share ONE GEMM with their weights
+    concatenated along N (a 128-wide GEMM runs at a third of the rate of a 640-wide one); each block reads its slice."""
+
+    def __init__(self):
+        self.groups = {}
+
+    def add(self, level, w, b):
+        g = self.groups.setdefault(level, [])
+        g.append((w, b))
+        return len(g) - 1
+
+    def finish(self):
+        self.w = {lv: torch.cat([w for w, _ in g], 0).contiguous() for lv, g in self.groups.items()}
+        self.b = {lv: torch.cat([b for _, b in g], 0).contiguous() for lv, g in self.groups.items()}
+        self.nh = {lv: g[0][0].shape[0] for lv, g in self.groups.items()}
+        self.groups = None
+
+    def run(self, ops, seg, width0):
+        """seg: {width: NHWC map}; -> {level: [T,h,w,n_blocks*nhidden]}"""
+        return {lv: ops.conv_gemm(seg[width0 >> lv], w, taps=TAPS_3X3, bias=self.b[lv], act=ACT_RELU)
+                for lv, w in self.w.items()}
+
+    def slice(self, all_actv, level, slot):
+        nh = self.nh[level]
+        return all_actv[level][..., slot * nh:(slot + 1) * nh]
 
 
 class _KVCache:
@@ -493,11 +526,15 @@ class InflatedUNetModelDualcondV2(_ModuleBase):
         self.kvc = _KVCache()
         self.time_embed = _TimeEmbed(P, "time_embed", self.cfg["model_channels"])
 
+        self.spade = _SpadeShared()
+        level = [0]                                    # resolution level of the layer being built (0 = input size)
+
         def build(p, l):
             if l[0] == "conv_in":
                 return ("conv_in", (P.f32(p + ".weight"), P.f32(p + ".bias")))
             if l[0] == "res":
-                return ("res", _ResBlock(P, p, l[1], l[2], True, self.emb), l[3] if len(l) > 3 else None)
+                return ("res", _ResBlock(P, p, l[1], l[2], True, self.emb, self.spade, level[0]),
+                        l[3] if len(l) > 3 else None)
             if l[0] == "st":
                 return ("st", _SpatialTransformer(P, p, l[1], l[2], self.kvc))
             if l[0] == "stconv":
@@ -505,8 +542,10 @@ class InflatedUNetModelDualcondV2(_ModuleBase):
             if l[0] == "tattn":
                 return ("tattn", _TemporalAttention(P, p, l[1], l[2], self.num_frames))
             if l[0] == "down":
+                level[0] += 1
                 return ("down", _Downsample(P, p))
             if l[0] == "up":
+                level[0] -= 1
                 return ("up", _Upsample(P, p))
             raise ValueError(l)
 
@@ -519,6 +558,8 @@ class InflatedUNetModelDualcondV2(_ModuleBase):
         self.out_b = P.f32("out.2.bias")
         self.emb.finish()
         self.kvc.finish()
+        self.spade.finish()
+        assert level[0] == 0
         self.loaded = True
         missing = [k for k in self.expected_shapes() if k not in sd]
         unexpected = [k for k in sd if k not in P.used]
@@ -534,7 +575,8 @@ class InflatedUNetModelDualcondV2(_ModuleBase):
             if kind == "conv_in":
                 h = ops.conv_small_cin(h, mod[0], mod[1])
             elif kind == "res":
-                h = mod(ops, h, emb_bias, seg[h.shape[2]], x2=h2, pool=self.pool)
+                h = mod(ops, h, emb_bias, seg[h.shape[2]], x2=h2, pool=self.pool,
+                        actv=self.spade.slice(self._actv, mod.sp_level, mod.sp_slot))
                 h2 = None
             elif kind == "st":
                 h = mod(ops, h, kv, self.kvc, pool=self.pool)
@@ -552,6 +594,7 @@ class InflatedUNetModelDualcondV2(_ModuleBase):
         emb = self.time_embed(ops, _t_scalar(timesteps, x.device))
         emb_bias = self.emb.run(ops, emb)
         kv = self.kvc.get(ops, context)
+        self._actv = self.spade.run(ops, seg, x.shape[3])
         hs, h = [], x.float().contiguous()
         for layers in self.input_blocks:
             h = self._run(layers, h, emb_bias, kv, seg)
@@ -559,6 +602,7 @@ class InflatedUNetModelDualcondV2(_ModuleBase):
         h = self._run(self.middle_block, h, emb_bias, kv, seg)
         for layers in self.output_blocks:
             h = self._run(layers, h, emb_bias, kv, seg, h2=hs.pop())   # th.cat([h, hs.pop()], dim=1) fused as 2 sources
+        self._actv = None
         a = _gn_silu(ops, h, self.out_norm, 1e-5, True)
         return ops.conv3x3_small_cout(a, self.out_w, self.out_b)       # (T, out_ch, H, W) fp32
 

@@ -169,7 +169,7 @@ def test_unet_two_clips_in_one_batch_vs_oracle():
     assert rel_err(both, ref) < 1e-2
     for k in range(2):
         alone = unet(x[k * T:(k + 1) * T], t, ctx, se(lat[k * T:(k + 1) * T], t))
-        assert rel_err(both[k * T:(k + 1) * T], alone) < 2e-3     # tile plans differ with the row count: fp16 rounding only
+        assert rel_err(both[k * T:(k + 1) * T], alone) < 5e-3     # tile plans differ with the row count: fp16 rounding only
 
 
 @pytest.mark.parametrize("use_graph", [False, True])

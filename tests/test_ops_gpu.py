@@ -210,7 +210,7 @@ def test_group_norm_single_launch(T, HW, C1, C2):
         assert torch.equal(got, O.group_norm(x1, g, b, 1e-5, True, x2=x2))
 
 
-@pytest.mark.parametrize("M,C", [(20480, 320), (5120, 640), (333, 1280), (7, 64)])
+@pytest.mark.parametrize("M,C", [(20480, 320), (5120, 640), (333, 1280), (7, 64), (65, 256), (19, 1024), (11, 2048), (9, 1536)])
 def test_layernorm(M, C):
     O = ops()
     x, g, b = (rnd(M, C) * 3 + 1).half(), rnd(C), rnd(C, seed=4)
@@ -240,6 +240,13 @@ def test_stem_and_head_convs():
     x = rnd(2, 4, 20, 28)
     w, b = rnd(64, 4, 3, 3, scale=0.2), rnd(64)
     assert rel_err(O.conv_small_cin(x, w, b), E.conv_small_cin(x, w, b)) < 2e-3
+    # the three instantiations (4x3x3, 3x3x3, run-time tap count), pixel counts that are not multiples of the 64-pixel
+    # batch or of the 4-pixel step, channel counts around the 128-channel chunk
+    for (n, ci, h, wd, co, ks) in [(3, 4, 13, 11, 320, 3), (1, 3, 17, 9, 128, 3), (2, 8, 7, 5, 200, 3), (2, 4, 9, 7, 64, 1),
+                                   (1, 1, 5, 5, 32, 3)]:
+        x = rnd(n, ci, h, wd, seed=n + ci)
+        w, b = rnd(co, ci, ks, ks, scale=0.2, seed=co), rnd(co, seed=ks)
+        assert rel_err(O.conv_small_cin(x, w, b), E.conv_small_cin(x, w, b)) < 2e-3, (n, ci, h, wd, co, ks)
     w1, b1 = rnd(8, 8, 1, 1, scale=0.3), rnd(8)
     x8 = rnd(2, 8, 9, 11)
     assert rel_err(O.conv_small_f32(x8, w1, b1), E.conv_small_f32(x8, w1, b1)) < 1e-5
