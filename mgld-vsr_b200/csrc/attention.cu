@@ -622,6 +622,8 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_launch_dependents();   // after the TMEM allocation (see conv_gemm.cu)
+  pdl_wait();                // q / k / v come from the preceding GEMM (see common.h)
   // kDbg = false folds every `if (dbg)` below away (the production instantiations)
   long long* const dbg = (kDbg && p.dbg) ? p.dbg + 16 * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
   const long long dbg_t0 = dbg ? clock64() : 0;
@@ -924,7 +926,7 @@ static int launch_attention_v3(const mgld_attention_desc* d, cudaStream_t stream
     attr_set = true;
   }
   dim3 grid(ceil_div(d->nq, 256), d->heads, d->batch);
-  kFns[p.dbg ? 3 : attn_v3_emu() / 2]<<<grid, kV3Threads, smem, stream>>>(tmQ, tmK, tmV, p);
+  MGLD_CUDA(launch_pdl(kFns[p.dbg ? 3 : attn_v3_emu() / 2], grid, dim3(kV3Threads), smem, stream, tmQ, tmK, tmV, p));
   MGLD_LAUNCH_CHECK("attention_v3_kernel");
   return MGLD_OK;
 }

@@ -57,4 +57,32 @@ int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* di
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch (PDL).  One DDPM tile-step is ~800 back-to-back kernels of 5-100 us in one stream / CUDA
+// graph; with ordinary stream order each boundary costs the launch latency plus the next kernel's prologue (block
+// scheduling, barrier init, TMEM allocation, tensor-map fetch) on an idle machine.  Kernels launched through launch_pdl()
+// may start while their predecessor drains: every such kernel calls pdl_launch_dependents() at its top (lets ITS successor
+// start early) and pdl_wait() before its first access to global memory (returns once all preceding grids have completed
+// and their writes are visible, so data hazards are exactly those of ordinary stream order).  MGLD_PDL=0 switches the
+// launch attribute off (the device instructions are then no-ops).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... P, typename... A>
+static inline cudaError_t launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+#endif
+
 }  // namespace mgld

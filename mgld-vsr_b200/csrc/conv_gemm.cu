@@ -198,6 +198,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  // Everything above (barrier init, TMEM allocation, descriptor prefetch) is independent of earlier kernels' output and
+  // overlaps the predecessor's tail; from here on global memory written by earlier kernels is read.  The trigger for
+  // the NEXT kernel comes only now, after this CTA owns its TMEM columns: a successor CTA that became co-resident and
+  // allocated first would hold the columns while waiting for this grid to finish.
+  pdl_launch_dependents();
+  pdl_wait();
   if (p.dbg && threadIdx.x == 0) { p.dbg[blockIdx.x * 16 + 12] = clock64() - dbg_k0; }
 
   // tile -> coordinates; consecutive tiles share the weight tile (n) and walk the pixel boxes (L2-friendly)
@@ -601,6 +607,9 @@ __device__ __forceinline__ float act1(float v, int act) {
   }
 }
 __global__ void splitk_finalize_kernel(const SplitFinalizeParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   const int vpr = (p.n_out_total + 7) >> 3;
   const long long M = static_cast<long long>(p.T) * p.H * p.W;
   const long long total = M * vpr;
@@ -770,7 +779,8 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
     const int pm = pair_mode_env();
     // a pair needs two M tiles.  Measured (profiles/r01_dev_run12*.log): pairs win on long-K convolutions with many M
     // tiles (VAE 256^2/512^2: +4..10%) and lose on short-K GEMMs and few-tile layers, so auto mode is conservative.
-    const bool big = p.tiles_m >= 512 && ntaps * p.kchunks >= 18;
+    static const int min_tiles = [] { const char* e = getenv("MGLD_CONV_PAIR_MIN_TILES"); return e ? atoi(e) : 512; }();
+    const bool big = p.tiles_m >= min_tiles && ntaps * p.kchunks >= 18;
     p.cta_pair = (p.tiles_m >= 2 && (pm == 1 || (pm < 0 && big))) ? 1 : 0;
   }
   const int workers = p.cta_pair ? sms / 2 : sms;
@@ -873,16 +883,18 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
   const int total_units = tiles_mw * p.tiles_n * p.split_k;
   if (!p.cta_pair) {
     dim3 grid(total_units < sms ? total_units : sms, 1, 1);
-    kernel<<<grid, kThreads, smem, stream>>>(tmA, tmA2, tmB, tmOut, tmRes, tmH, p);
+    MGLD_CUDA(launch_pdl(kernel, grid, dim3(kThreads), smem, stream, tmA, tmA2, tmB, tmOut, tmRes, tmH, p));
   } else {
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     if (g_max_pairs < 0) {
       cfg.gridDim = dim3(2 * (sms / 2), 1, 1);
       cfg.dynamicSmemBytes = 226 * 1024;
@@ -969,7 +981,7 @@ static int conv_gemm_dispatch(const mgld_conv_gemm_desc* d, void* stream_) {
   MGLD_CHECK_ARG(f.n_out_total % 8 == 0, "conv_gemm(split-K): output columns must be a multiple of 8");
   const long long total = (long long)d->T * d->H * d->W * (f.n_out_total / 8);
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  splitk_finalize_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(f);
+  MGLD_CUDA(launch_pdl(splitk_finalize_kernel, dim3(blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_), f));
   MGLD_LAUNCH_CHECK("splitk_finalize_kernel");
   return MGLD_OK;
 }

@@ -19,6 +19,9 @@ namespace mgld {
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, __half* __restrict__ out, int C, int HW, int ldo,
                                     float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -34,6 +37,9 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, __half* __rest
 }
 __global__ void nhwc_to_nchw_kernel(const __half* __restrict__ in, float* __restrict__ out, int C, int HW, int ldi,
                                     float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -52,6 +58,9 @@ __global__ void nhwc_to_nchw_kernel(const __half* __restrict__ in, float* __rest
 // nearest 2x upsample, NHWC fp16 (one 16-byte vector per thread)
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int T, int H, int W, int vpr) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   const long long total = static_cast<long long>(T) * 4 * H * W * vpr;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int v = i % vpr;
@@ -70,6 +79,9 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restric
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void im2col_s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int T, int H, int W, int Ho,
                                  int Wo, int vpr, int pad) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   const long long total = static_cast<long long>(T) * Ho * Wo * 9 * vpr;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int v = i % vpr;
@@ -98,6 +110,9 @@ template <int kK4>
 __global__ void __launch_bounds__(128)
 conv_small_cin_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                       __half* __restrict__ out, int N, int Cin, int H, int W, int Cout, int ks, int ldo) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   __shared__ __align__(16) float patch[kScPix][76];   // 72 taps max, padded to float4 rows
   const int K = Cin * ks * ks, pad = ks / 2;
   const long long total = static_cast<long long>(N) * H * W;
@@ -231,6 +246,9 @@ __device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v))
 __global__ void gemv_kernel(const float* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
                             const float* __restrict__ add, float* __restrict__ y, int N, int K, int silu_in,
                             int silu_out) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= N) return;
   float acc = 0.f;
@@ -256,6 +274,9 @@ __global__ void gemv_kernel(const float* __restrict__ x, const __half* __restric
 
 // timestep_embedding (util.py:151-171): emb[i] = cos(t*f_i), emb[half+i] = sin(t*f_i), f_i = exp(-ln(max_period)*i/half)
 __global__ void timestep_embedding_kernel(const float* __restrict__ tp, float* __restrict__ out, int dim, float max_period) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   const float t = *tp;
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -273,6 +294,9 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ tp, float* _
 constexpr int kMaxT = 8;
 __global__ void temporal_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int T, int HW, int C,
                                           int heads, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= static_cast<long long>(HW) * heads) return;
@@ -370,7 +394,7 @@ extern "C" int mgld_nchw_f32_to_nhwc_f16(const float* in, void* out, int n, int 
                                          void* stream) {
   MGLD_CHECK_ARG(in && out && n > 0 && c > 0 && h > 0 && w > 0, "nchw_to_nhwc: bad arguments");
   dim3 grid(ceil_div(h * w, 32), ceil_div(c, 32), n), block(32, 8);
-  nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, (__half*)out, c, h * w, ldo > 0 ? ldo : c, scale);
+  MGLD_CUDA(launch_pdl(nchw_to_nhwc_kernel, grid, block, 0, (cudaStream_t)stream, in, (__half*)out, c, h * w, ldo > 0 ? ldo : c, scale));
   MGLD_LAUNCH_CHECK("nchw_to_nhwc_kernel");
   return MGLD_OK;
 }
@@ -378,14 +402,14 @@ extern "C" int mgld_nhwc_f16_to_nchw_f32(const void* in, float* out, int n, int 
                                          void* stream) {
   MGLD_CHECK_ARG(in && out && n > 0 && c > 0 && h > 0 && w > 0, "nhwc_to_nchw: bad arguments");
   dim3 grid(ceil_div(h * w, 32), ceil_div(c, 32), n), block(32, 8);
-  nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __half*)in, out, c, h * w, ldi > 0 ? ldi : c, scale);
+  MGLD_CUDA(launch_pdl(nhwc_to_nchw_kernel, dim3(grid), dim3(block), 0, (cudaStream_t)stream, (const __half*)in, out, c, h * w, ldi > 0 ? ldi : c, scale));
   MGLD_LAUNCH_CHECK("nhwc_to_nchw_kernel");
   return MGLD_OK;
 }
 extern "C" int mgld_upsample_nearest2x_f16(const void* in, void* out, int t, int h, int w, int c, void* stream) {
   MGLD_CHECK_ARG(in && out && c % 8 == 0 && t > 0 && h > 0 && w > 0, "upsample2x: bad arguments");
   const long long total = 4LL * t * h * w * (c / 8);
-  upsample2x_kernel<<<grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, t, h, w, c / 8);
+  MGLD_CUDA(launch_pdl(upsample2x_kernel, dim3(grid_1d(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const uint4*)in, (uint4*)out, t, h, w, c / 8));
   MGLD_LAUNCH_CHECK("upsample2x_kernel");
   return MGLD_OK;
 }
@@ -393,7 +417,7 @@ extern "C" int mgld_im2col_s2_f16(const void* in, void* out, int t, int h, int w
                                   void* stream) {
   MGLD_CHECK_ARG(in && out && c % 8 == 0 && t > 0 && ho > 0 && wo > 0 && (pad == 0 || pad == 1), "im2col_s2: bad arguments");
   const long long total = 9LL * t * ho * wo * (c / 8);
-  im2col_s2_kernel<<<grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, t, h, w, ho, wo, c / 8, pad);
+  MGLD_CUDA(launch_pdl(im2col_s2_kernel, dim3(grid_1d(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const uint4*)in, (uint4*)out, t, h, w, ho, wo, c / 8, pad));
   MGLD_LAUNCH_CHECK("im2col_s2_kernel");
   return MGLD_OK;
 }
@@ -404,9 +428,9 @@ extern "C" int mgld_conv_small_cin_f32(const float* in, const float* w, const fl
   dim3 grid((unsigned)((total + kScPix - 1) / kScPix), (unsigned)ceil_div(cout, 128));
   const int K = cin * ks * ks, ld = ldo > 0 ? ldo : cout;
   cudaStream_t st = (cudaStream_t)stream;
-  if (K == 36) conv_small_cin_kernel<9><<<grid, 128, 0, st>>>(in, w, bias, (__half*)out, n, cin, h, wd, cout, ks, ld);
-  else if (K == 27) conv_small_cin_kernel<7><<<grid, 128, 0, st>>>(in, w, bias, (__half*)out, n, cin, h, wd, cout, ks, ld);
-  else conv_small_cin_kernel<0><<<grid, 128, 0, st>>>(in, w, bias, (__half*)out, n, cin, h, wd, cout, ks, ld);
+  if (K == 36) MGLD_CUDA(launch_pdl(conv_small_cin_kernel<9>, dim3(grid), dim3(128), 0, st, in, w, bias, (__half*)out, n, cin, h, wd, cout, ks, ld));
+  else if (K == 27) MGLD_CUDA(launch_pdl(conv_small_cin_kernel<7>, dim3(grid), dim3(128), 0, st, in, w, bias, (__half*)out, n, cin, h, wd, cout, ks, ld));
+  else MGLD_CUDA(launch_pdl(conv_small_cin_kernel<0>, dim3(grid), dim3(128), 0, st, in, w, bias, (__half*)out, n, cin, h, wd, cout, ks, ld));
   MGLD_LAUNCH_CHECK("conv_small_cin_kernel");
   return MGLD_OK;
 }
@@ -441,13 +465,13 @@ extern "C" int mgld_conv3x3_small_cout_f16(const void* in, const void* w, const 
 extern "C" int mgld_gemv_f32(const float* x, const void* w, const float* bias, const float* add, float* y, int n, int k,
                              int silu_in, int silu_out, void* stream) {
   MGLD_CHECK_ARG(x && w && y && n > 0 && k > 0 && k % 8 == 0, "gemv: bad arguments");
-  gemv_kernel<<<ceil_div(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, (const __half*)w, bias, add, y, n, k, silu_in, silu_out);
+  MGLD_CUDA(launch_pdl(gemv_kernel, dim3(ceil_div(n * 32, 256)), dim3(256), 0, (cudaStream_t)stream, x, (const __half*)w, bias, add, y, n, k, silu_in, silu_out));
   MGLD_LAUNCH_CHECK("gemv_kernel");
   return MGLD_OK;
 }
 extern "C" int mgld_timestep_embedding_f32(const float* t, float* out, int dim, float max_period, void* stream) {
   MGLD_CHECK_ARG(t && out && dim > 0 && dim % 2 == 0, "timestep_embedding: bad arguments");
-  timestep_embedding_kernel<<<ceil_div(dim / 2, 128), 128, 0, (cudaStream_t)stream>>>(t, out, dim, max_period);
+  MGLD_CUDA(launch_pdl(timestep_embedding_kernel, dim3(ceil_div(dim / 2, 128)), dim3(128), 0, (cudaStream_t)stream, t, out, dim, max_period));
   MGLD_LAUNCH_CHECK("timestep_embedding_kernel");
   return MGLD_OK;
 }
@@ -455,7 +479,7 @@ extern "C" int mgld_temporal_attention_f16(const void* qkv, void* out, int t, in
                                            void* stream) {
   MGLD_CHECK_ARG(qkv && out && t > 0 && t <= kMaxT && c == heads * 64, "temporal_attention: T=%d (max %d), C=%d, heads=%d (head_dim must be 64)", t, kMaxT, c, heads);
   const long long warps = 1LL * hw * heads;
-  temporal_attention_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __half*)qkv, (__half*)out, t, hw, c, heads, scale);
+  MGLD_CUDA(launch_pdl(temporal_attention_kernel, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, (const __half*)qkv, (__half*)out, t, hw, c, heads, scale));
   MGLD_LAUNCH_CHECK("temporal_attention_kernel");
   return MGLD_OK;
 }

@@ -44,6 +44,9 @@ constexpr int kGnApplyItems = 1024;  // 8-channel vectors per block in gn_apply
 // sums[t][g] += (sum, sumsq) over rows [r0, r0+64) of frame t.  Double accumulation across blocks.
 __global__ void gn_stats_kernel(const __half* __restrict__ x1, int C1, int ld1, const __half* __restrict__ x2, int C2,
                                 int ld2, int HW, int G, double* __restrict__ sums) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   extern __shared__ float sh[];  // [2*G]
   const int C = C1 + C2, vpr = C >> 3, cpg = C / G;
   const int t = blockIdx.y;
@@ -96,6 +99,9 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, int C1, int ld1, 
 // (sum, sumsq) -> (mean, rstd) fp32
 __global__ void gn_finalize_kernel(const double* __restrict__ sums, float* __restrict__ stats, int n, double count,
                                    double eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double mean = sums[2 * i] / count;
@@ -110,6 +116,9 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, int ld1, 
                                 int ld2, int HW, int G, const double* __restrict__ sums, double eps,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
                                 __half* __restrict__ out, int ldo) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   extern __shared__ float sh[];  // [2*G] mean, rstd
   const int C = C1 + C2, vpr = C >> 3, cpg = C / G;
   const int t = blockIdx.y;
@@ -213,6 +222,9 @@ __device__ __forceinline__ float ld_shared_cluster_f32(uint32_t addr) {
 
 template <int kItems>
 __global__ void __launch_bounds__(kGnFusedThreads, 1) gn_fused_kernel(const GnFusedParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   extern __shared__ float tab[];                  // [2][R][cc]: per-thread channel partials (sum | sumsq)
   __shared__ float chs[2 * kGnFusedThreads];      // per-channel (sum | sumsq) of this CTA's patch
   __shared__ float part[2 * kGnFusedMaxGroups];   // this CTA's partial (sum, sumsq) per local group
@@ -333,6 +345,9 @@ template <int kVec>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __half* __restrict__ x, int ldx, int M, int C, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __half* __restrict__ out, int ldo) {
+  pdl_launch_dependents();
+  pdl_wait();
+
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= M) return;
   const int vpr = C >> 3;
@@ -419,8 +434,8 @@ extern "C" int mgld_gn_stats_f16(const void* x1, int C1, int ld1, const void* x2
                  groups);
   MGLD_CHECK_ARG((C2 > 0) == (x2 != nullptr), "gn_stats: x2/C2 mismatch");
   dim3 grid(ceil_div(HW, kGnRowsPerBlock), T);
-  gn_stats_kernel<<<grid, gn_threads(C), 2 * groups * sizeof(float), (cudaStream_t)stream>>>(
-      (const __half*)x1, C1, ld1 > 0 ? ld1 : C1, (const __half*)x2, C2, ld2 > 0 ? ld2 : C2, HW, groups, sums);
+  MGLD_CUDA(launch_pdl(gn_stats_kernel, grid, dim3(gn_threads(C)), 2 * groups * sizeof(float), (cudaStream_t)stream,
+                       (const __half*)x1, C1, ld1 > 0 ? ld1 : C1, (const __half*)x2, C2, ld2 > 0 ? ld2 : C2, HW, groups, sums));
   MGLD_LAUNCH_CHECK("gn_stats_kernel");
   return MGLD_OK;
 }
@@ -429,7 +444,8 @@ extern "C" int mgld_gn_finalize(const double* sums, float* stats, int T, int gro
                                 void* stream) {
   MGLD_CHECK_ARG(sums && stats && T > 0 && groups > 0, "gn_finalize: bad arguments");
   const int n = T * groups;
-  gn_finalize_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(sums, stats, n, (double)HW * (C / groups), eps);
+  MGLD_CUDA(launch_pdl(gn_finalize_kernel, dim3(ceil_div(n, 128)), dim3(128), 0, (cudaStream_t)stream, sums, stats, n,
+                       (double)HW * (C / groups), eps));
   MGLD_LAUNCH_CHECK("gn_finalize_kernel");
   return MGLD_OK;
 }
@@ -451,9 +467,9 @@ extern "C" int mgld_gn_apply_f16(const void* x1, int C1, int ld1, const void* x2
   const long long resident = static_cast<long long>(num_sms()) * occ / T;   // one wave: T frames share the machine
   if (bx > resident && resident >= 1) bx = resident;
   dim3 grid((unsigned)bx, T);
-  gn_apply_kernel<<<grid, 256, 2 * groups * sizeof(float), (cudaStream_t)stream>>>(
-      (const __half*)x1, C1, ld1 > 0 ? ld1 : C1, (const __half*)x2, C2, ld2 > 0 ? ld2 : C2, HW, groups, sums, eps,
-      gamma, beta, silu, (__half*)out, ldo > 0 ? ldo : C);
+  MGLD_CUDA(launch_pdl(gn_apply_kernel, grid, dim3(256), 2 * groups * sizeof(float), (cudaStream_t)stream,
+                       (const __half*)x1, C1, ld1 > 0 ? ld1 : C1, (const __half*)x2, C2, ld2 > 0 ? ld2 : C2, HW, groups, sums, eps,
+                       gamma, beta, silu, (__half*)out, ldo > 0 ? ldo : C));
   MGLD_LAUNCH_CHECK("gn_apply_kernel");
   return MGLD_OK;
 }
@@ -515,14 +531,16 @@ extern "C" int mgld_group_norm_f16(const void* x1, int C1, int ld1, const void* 
   p.HW = HW; p.G = groups; p.eps = eps; p.gamma = gamma; p.beta = beta; p.silu = silu;
   p.out = (__half*)out; p.ldo = ldo; p.stats_out = stats_out;
   cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = p.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.gridDim = dim3(p.cs, csplit, T);
   cfg.blockDim = dim3(p.vpc * p.R, 1, 1);
   cfg.dynamicSmemBytes = 2 * p.R * p.cc * sizeof(float);   // <= 32 KB (R * cc <= 512 * 8)
   cfg.stream = (cudaStream_t)stream;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   if (items <= 2) MGLD_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_kernel<2>, p));
   else if (items <= 4) MGLD_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_kernel<4>, p));
   else if (items <= 8) MGLD_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_kernel<8>, p));
@@ -543,11 +561,11 @@ extern "C" int mgld_layernorm_f16(const void* x, int ldx, int M, int C, const fl
   __half* op = (__half*)out;
   const int lx = ldx > 0 ? ldx : C, lo = ldo > 0 ? ldo : C;
   switch (vec) {
-    case 1: layernorm_kernel<1><<<grid, block, 0, st>>>(xp, lx, M, C, gamma, beta, eps, op, lo); break;
-    case 2: layernorm_kernel<2><<<grid, block, 0, st>>>(xp, lx, M, C, gamma, beta, eps, op, lo); break;
-    case 3: layernorm_kernel<3><<<grid, block, 0, st>>>(xp, lx, M, C, gamma, beta, eps, op, lo); break;
-    case 4: case 5: layernorm_kernel<5><<<grid, block, 0, st>>>(xp, lx, M, C, gamma, beta, eps, op, lo); break;
-    default: layernorm_kernel<kLnMaxVec><<<grid, block, 0, st>>>(xp, lx, M, C, gamma, beta, eps, op, lo); break;
+    case 1: MGLD_CUDA(launch_pdl(layernorm_kernel<1>, grid, block, 0, st, xp, lx, M, C, gamma, beta, eps, op, lo)); break;
+    case 2: MGLD_CUDA(launch_pdl(layernorm_kernel<2>, grid, block, 0, st, xp, lx, M, C, gamma, beta, eps, op, lo)); break;
+    case 3: MGLD_CUDA(launch_pdl(layernorm_kernel<3>, grid, block, 0, st, xp, lx, M, C, gamma, beta, eps, op, lo)); break;
+    case 4: case 5: MGLD_CUDA(launch_pdl(layernorm_kernel<5>, grid, block, 0, st, xp, lx, M, C, gamma, beta, eps, op, lo)); break;
+    default: MGLD_CUDA(launch_pdl(layernorm_kernel<kLnMaxVec>, grid, block, 0, st, xp, lx, M, C, gamma, beta, eps, op, lo)); break;
   }
   MGLD_LAUNCH_CHECK("layernorm_kernel");
   return MGLD_OK;

@@ -1,4 +1,5 @@
 // Library state: error string, driver entry points, device properties.
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/mgld.h"
@@ -24,6 +25,10 @@ int cuda_fail(cudaError_t e, const char* what) {
 EncodeTiledFn encode_tiled_fn() { return g_encode; }
 int num_sms() { return g_num_sms; }
 bool initialised() { return g_init; }
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("MGLD_PDL"); return !e || atoi(e) != 0; }();
+  return on;
+}
 
 int make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box, const uint32_t* elem_strides) {

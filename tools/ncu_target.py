@@ -1,4 +1,4 @@
-"""Profiling target: one eager (no CUDA graph) struct-encoder + UNet tile-step at the SD-2.1 shapes (T=5, 64x64 latent).
+"""Profiling target: one eager (no CUDA graph) struct-encoder + UNet tile-step at the SD-2.1 shapes (MGLD_T frames, 64x64 latent).
 Run under ncu:  ncu ... python tools/ncu_target.py [n_steps]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,7 +10,7 @@ cfg = load_cfg(); dev = "cuda"
 mp = cfg.model.params
 unet = instantiate_from_config(mp.unet_config); se = instantiate_from_config(mp.structcond_stage_config)
 unet.load_state_dict(fast_state_dict(unet.expected_shapes(), 0)); se.load_state_dict(fast_state_dict(se.expected_shapes(), 1))
-T = 5
+T = int(os.environ.get("MGLD_T", "5"))   # frames in the (b t) batch: 5 = one clip, 10 = the bench's two clips
 x = torch.randn(T, 4, 64, 64, device=dev); lat = torch.randn(T, 4, 64, 64, device=dev)
 ctx = torch.randn(1, 77, 1024, device=dev); t = torch.tensor([500], device=dev)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2
