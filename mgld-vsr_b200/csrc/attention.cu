@@ -38,6 +38,8 @@ struct AttnParams {
   __half* out;
   int ldo;                           // out row pitch (elements); out[(b*nq + i)*ldo + h*DH + d]
   int seq;                           // v3: the two softmax warpgroups take turns on the exponential section
+  int stagger;                       // v3: cycles by which query tile 1 starts behind tile 0 (0 = none)
+  int nomax;                         // v3: skip the row max after the first key block (overflow-checked, see the kernel)
   long long* dbg;                    // optional per-CTA cycle counters [CTAs][16] (mgld_attention_set_debug_counters); null in production
 };
 
@@ -764,62 +766,87 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int u = 0; u < kKVTile; ++u)
           if (u >= kv_left) sc[u] = -INFINITY;
       }
-      float mx0 = sc[0], mx1 = sc[1], mx2 = sc[2], mx3 = sc[3];
+      auto row_max = [&]() {
+        float mx0 = sc[0], mx1 = sc[1], mx2 = sc[2], mx3 = sc[3];
 #pragma unroll
-      for (int u = 4; u < kKVTile; u += 8) {
-        mx0 = fmaxf(mx0, fmaxf(sc[u], sc[u + 1]));
-        mx1 = fmaxf(mx1, fmaxf(sc[u + 2], sc[u + 3]));
-        if (u + 4 < kKVTile) {
-          mx2 = fmaxf(mx2, fmaxf(sc[u + 4], sc[u + 5]));
-          mx3 = fmaxf(mx3, fmaxf(sc[u + 6], sc[u + 7]));
+        for (int u = 4; u < kKVTile; u += 8) {
+          mx0 = fmaxf(mx0, fmaxf(sc[u], sc[u + 1]));
+          mx1 = fmaxf(mx1, fmaxf(sc[u + 2], sc[u + 3]));
+          if (u + 4 < kKVTile) {
+            mx2 = fmaxf(mx2, fmaxf(sc[u + 4], sc[u + 5]));
+            mx3 = fmaxf(mx3, fmaxf(sc[u + 6], sc[u + 7]));
+          }
         }
-      }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      // lazy max update: only move the reference max when it grew by more than 8 in the exp2 domain
-      float alpha = 1.f;
-      const bool grow = (mx - m_run) * k2 > 8.f;   // also true on the first block (m_run = -inf)
-      if (grow) {
-        alpha = ex2_approx((m_run - mx) * k2);      // 0 on the first block
-        m_run = mx;
-      }
-      const float nmk = -m_run * k2;
-      if (p.seq && (i == 1 || j > 0)) wait_t(smem_u32(&exp_turn[i ^ 1]), (i == 1 ? j : j - 1) & 1, w_seq);
+        return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      };
+      auto rescale_o = [&](const float a) {
+#pragma unroll
+        for (int o0 = 0; o0 < DH; o0 += 16) {
+          uint32_t r[16];
+          tmem_ld_x16(orow + o0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 16; ++u) r[u] = __float_as_uint(__uint_as_float(r[u]) * a);
+          tmem_st_x16(orow + o0, r);
+        }
+      };
+      // P = exp2(s * k2 - m_run * k2) as fp16 pairs into TMEM, row sum into rs0 + rs1.  `first_pass`: the wait for PV_i(j-1)
+      // (P_i may only be overwritten and O_i rescaled once it is complete) sits behind the first chunk of exponentials —
+      // by then the PV issued at the end of the previous block has long finished — followed by the pending rescale.
       float rs0 = 0.f, rs1 = 0.f;
-      const long long t_exp = dbg ? clock64() : 0;
+      auto exp_store = [&](const float nmk, const bool first_pass, const bool rescale, const float a) {
+        rs0 = 0.f; rs1 = 0.f;
 #pragma unroll
-      for (int c0 = 0; c0 < kKVTile; c0 += 32) {
-        uint32_t pk[16];
+        for (int c0 = 0; c0 < kKVTile; c0 += 32) {
+          uint32_t pk[16];
 #pragma unroll
-        for (int u = 0; u < 32; u += 2) {
-          float x0, x1, e0, e1;
-          ffma2(x0, x1, sc[c0 + u], sc[c0 + u + 1], k2, k2, nmk, nmk);
-          if (((u >> 1) & 3) < kEmu / 2) {          // kEmu of every 8 exponentials on the FMA pipe
-            exp2_poly2(e0, e1, x0, x1);
-          } else {
-            e0 = ex2_approx(x0);
-            e1 = ex2_approx(x1);
-          }
-          fadd2(rs0, rs1, rs0, rs1, e0, e1);
-          pk[u >> 1] = pack_h2(e0, e1);
-        }
-        if (c0 == 0 && j > 0) {
-          // P_i may only be overwritten (and O_i rescaled) once PV_i(j-1) is complete.  The wait sits behind the first
-          // chunk of exponentials: by then the PV issued at the end of the previous block has long finished.
-          wait_t(smem_u32(&pv_done[i]), (j - 1) & 1, w_pv);
-          tc_fence_after();
-          if (__any_sync(0xffffffffu, grow)) {
-#pragma unroll
-            for (int o0 = 0; o0 < DH; o0 += 16) {
-              uint32_t r[16];
-              tmem_ld_x16(orow + o0, r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int u = 0; u < 16; ++u) r[u] = __float_as_uint(__uint_as_float(r[u]) * alpha);
-              tmem_st_x16(orow + o0, r);
+          for (int u = 0; u < 32; u += 2) {
+            float x0, x1, e0, e1;
+            ffma2(x0, x1, sc[c0 + u], sc[c0 + u + 1], k2, k2, nmk, nmk);
+            if (((u >> 1) & 3) < kEmu / 2) {          // kEmu of every 8 exponentials on the FMA pipe
+              exp2_poly2(e0, e1, x0, x1);
+            } else {
+              e0 = ex2_approx(x0);
+              e1 = ex2_approx(x1);
             }
+            fadd2(rs0, rs1, rs0, rs1, e0, e1);
+            pk[u >> 1] = pack_h2(e0, e1);
           }
+          if (c0 == 0 && first_pass && j > 0) {
+            wait_t(smem_u32(&pv_done[i]), (j - 1) & 1, w_pv);
+            tc_fence_after();
+            if (__any_sync(0xffffffffu, rescale)) rescale_o(a);
+          }
+          tmem_st_x16(prow + (c0 >> 1), pk);
         }
-        tmem_st_x16(prow + (c0 >> 1), pk);
+      };
+      float alpha = 1.f;
+      if (p.seq && (i == 1 || j > 0)) wait_t(smem_u32(&exp_turn[i ^ 1]), (i == 1 ? j : j - 1) & 1, w_seq);
+      const long long t_exp = dbg ? clock64() : 0;
+      if (!p.nomax || j == 0) {
+        // lazy max update: only move the reference max when it grew by more than 8 in the exp2 domain
+        const float mx = row_max();
+        const bool grow = (mx - m_run) * k2 > 8.f;   // also true on the first block (m_run = -inf)
+        if (grow) {
+          alpha = ex2_approx((m_run - mx) * k2);      // 0 on the first block
+          m_run = mx;
+        }
+        exp_store(-m_run * k2, true, grow, alpha);
+      } else {
+        // No row max at all after the first block: any reference m_run gives the same softmax as long as no exponential
+        // overflows fp16.  The exponentials are non-negative, so a row sum below 2^15 bounds every one of them; only when
+        // the scores outgrew the reference by a factor > 2^15 (rare) is the block redone with the true max.
+        exp_store(-m_run * k2, true, false, 1.f);
+        const bool over = !(rs0 + rs1 < 32768.f);
+        if (__any_sync(0xffffffffu, over)) {
+          const float mx = row_max();
+          if (mx > m_run) {
+            alpha = ex2_approx((m_run - mx) * k2);
+            m_run = mx;
+          }
+          rescale_o(alpha);                           // PV_i(j-1) is complete (waited for in the first pass)
+          exp_store(-m_run * k2, false, false, 1.f);
+        }
       }
       if (p.seq) { __syncwarp(); if (lane == 0) mbar_arrive(smem_u32(&exp_turn[i])); }
       if (dbg) c_exp += clock64() - t_exp;
@@ -832,6 +859,10 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (has_next) scores_loaded();
     };
     const int nfull = p.nkv / kKVTile;
+    if (i == 1 && p.stagger > 0) {   // de-phase the two tiles: tile 1's block boundaries (PV / S bursts on the tensor pipe,
+      const long long t0 = clock64();   // max + barrier phases) then fall into tile 0's exponential phase and vice versa
+      while (clock64() - t0 < p.stagger) {}
+    }
     load_scores(0);
     scores_loaded();
     for (int j = 0; j < nfull; ++j) block(j, std::false_type{}, j + 1 < nblk);
@@ -873,6 +904,7 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }
 
 static long long* g_attn_dbg = nullptr;
+static bool nkv_blocks_for_stagger(int nkv) { return nkv > 4 * kKVTile; }   // pointless for a handful of key blocks
 
 static int attn_v3_emu() {   // exponentials per 8 evaluated on the FMA pipe: MGLD_ATTN_EMU = 0, 2 or 4
   static int v = -1;
@@ -898,6 +930,12 @@ static int launch_attention_v3(const mgld_attention_desc* d, cudaStream_t stream
     static int seq = -1;
     if (seq < 0) { const char* e = getenv("MGLD_ATTN_SEQ"); seq = e ? (atoi(e) != 0) : 0; }   // off: measured slower (profiles/r01_dev_run21*)
     p.seq = seq;
+    static int stagger = -1;
+    if (stagger < 0) { const char* e = getenv("MGLD_ATTN_STAGGER"); stagger = e ? atoi(e) : 0; }
+    p.stagger = nkv_blocks_for_stagger(d->nkv) ? stagger : 0;
+    static int nomax = -1;
+    if (nomax < 0) { const char* e = getenv("MGLD_ATTN_NOMAX"); nomax = e ? (atoi(e) != 0) : 1; }
+    p.nomax = nomax;
   }
   CUtensorMap tmQ, tmK, tmV;
   {

@@ -606,3 +606,41 @@ def convex_upsample8(mask, flow):
     _count(1)
     _L.check(_L.lib().mgld_convex_upsample8_f32(_L.ptr(mask), _L.ptr(flow), _L.ptr(out), b, h, w, _L.stream_ptr()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CUDA-graph replay of a launch-bound host graph (RAFT: ~700 small launches per call)
+# ---------------------------------------------------------------------------------------------------------------
+class GraphedFn:
+    """Captures `fn(*tensors) -> tensor` once per input signature (shapes / dtypes) and replays the graph afterwards.
+    The function must be free of host synchronisation and of data-dependent control flow.  Inputs are copied into
+    static buffers, the result is returned as a fresh tensor."""
+
+    def __init__(self, fn, use_graph=True, warmup=1):
+        self.fn, self.use_graph, self.warmup = fn, use_graph, warmup
+        self.graphs = {}
+
+    def __call__(self, *xs):
+        if not (self.use_graph and all(x.is_cuda for x in xs)) or torch.cuda.is_current_stream_capturing():
+            return self.fn(*xs)
+        key = tuple((tuple(x.shape), x.dtype) for x in xs)
+        g = self.graphs.get(key)
+        if g is None:
+            static = [x.clone() for x in xs]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(self.warmup):                     # lazy init, caching-allocator warm-up
+                    self.fn(*static)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            n0 = LAUNCHES[0]
+            with torch.cuda.graph(graph):
+                out = self.fn(*static)
+            g = self.graphs[key] = (graph, static, out, LAUNCHES[0] - n0)
+        graph, static, out, n_kernels = g
+        for s_, x in zip(static, xs):
+            s_.copy_(x)
+        graph.replay()
+        LAUNCHES[0] += n_kernels
+        return out.clone()

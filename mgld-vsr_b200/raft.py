@@ -202,9 +202,20 @@ class RAFT_SR(_ModuleBase):
     # ---- forward (raft_arch.py:733-808) ---------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, ref, sup, iters=10, flow_init=None, upsample=True):
+        """The ~700 launches of one call are tiny (h/8 x w/8 maps): on CUDA they are replayed from a graph captured per
+        input shape (`use_cuda_graph`, default on)."""
         assert self.loaded, "load_state_dict() first"
         assert ref.size() == sup.size()                                   # raft_arch.py:800
         assert flow_init is None
+        if ref.is_cuda and getattr(self, "use_cuda_graph", True) and hasattr(self.ops, "GraphedFn"):
+            runner = self.__dict__.get("_graphed")
+            if runner is None or runner[0] != iters:
+                fn = self.ops.GraphedFn(lambda a, b: self._forward(a, b, iters))
+                runner = self.__dict__["_graphed"] = (iters, fn)
+            return runner[1](ref.float().contiguous(), sup.float().contiguous())
+        return self._forward(ref, sup, iters)
+
+    def _forward(self, ref, sup, iters=10):
         ops = self.ops
         ops.stats_pool_reset()
         ht, wd = ref.shape[-2:]
