@@ -4,9 +4,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from mgld_vsr_b200 import ops, lib as L
 dev = "cuda"
+import os
+shapes_t10 = [(10, 64, 64, 320, 320, 1, 0), (10, 64, 64, 320, 960, 1, 0), (10, 64, 64, 1280, 320, 1, 0), (10, 32, 32, 640, 640, 1, 0),
+              (10, 16, 16, 1280, 1280, 1, 0), (10, 64, 64, 320, 320, 9, 0), (10, 16, 16, 1280, 1280, 9, 0), (10, 8, 8, 1280, 1280, 9, 0)]
 shapes = [(5, 64, 64, 320, 320, 9, 0), (5, 64, 64, 320, 320, 1, 0), (5, 64, 64, 320, 960, 1, 0), (5, 64, 64, 320, 2560, 1, 0),
           (5, 64, 64, 320, 2560, 1, 128), (5, 64, 64, 1280, 320, 1, 0), (5, 32, 32, 640, 640, 1, 0), (5, 32, 32, 640, 5120, 1, 0),
           (5, 16, 16, 1280, 1280, 1, 0), (5, 256, 256, 256, 256, 9, 0)]
+if os.environ.get("MGLD_T") == "10": shapes = shapes_t10
 so = L.lib()
 so.mgld_conv_gemm_set_debug_counters.argtypes = [ctypes.c_void_p]
 so.mgld_conv_gemm_set_debug_counters.restype = None
