@@ -777,9 +777,10 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
   const int sms = num_sms();
   {
     const int pm = pair_mode_env();
-    // a pair needs two M tiles.  Measured (profiles/r01_dev_run12*.log): pairs win on long-K convolutions with many M
-    // tiles (VAE 256^2/512^2: +4..10%) and lose on short-K GEMMs and few-tile layers, so auto mode is conservative.
-    static const int min_tiles = [] { const char* e = getenv("MGLD_CONV_PAIR_MIN_TILES"); return e ? atoi(e) : 512; }();
+    // a pair needs two M tiles.  Measured: pairs win on long-K convolutions (K >= 18 chunks) and lose on short-K GEMMs
+    // (profiles/r01_dev_run12*.log); with the M-tile threshold at 64 instead of 512 the batched UNet tile-step gains 2 % and
+    // the VAE decode 6 % (profiles/r01_dev_run35*.log).
+    static const int min_tiles = [] { const char* e = getenv("MGLD_CONV_PAIR_MIN_TILES"); return e ? atoi(e) : 64; }();
     const bool big = p.tiles_m >= min_tiles && ntaps * p.kchunks >= 18;
     p.cta_pair = (p.tiles_m >= 2 && (pm == 1 || (pm < 0 && big))) ? 1 : 0;
   }
