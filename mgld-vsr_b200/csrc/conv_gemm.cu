@@ -778,10 +778,11 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
   {
     const int pm = pair_mode_env();
     // a pair needs two M tiles.  Measured: pairs win on long-K convolutions (K >= 18 chunks) and lose on short-K GEMMs
-    // (profiles/r01_dev_run12*.log); with the M-tile threshold at 64 instead of 512 the batched UNet tile-step gains 2 % and
-    // the VAE decode 6 % (profiles/r01_dev_run35*.log).
-    static const int min_tiles = [] { const char* e = getenv("MGLD_CONV_PAIR_MIN_TILES"); return e ? atoi(e) : 64; }();
-    const bool big = p.tiles_m >= min_tiles && ntaps * p.kchunks >= 18;
+    // (profiles/r01_dev_run12*.log); with the M-tile threshold at 16 instead of 512 the batched UNet tile-step gains 2 % and
+    // the VAE decode 3-6 % (profiles/r01_dev_run35*.log, r01_dev_run36*.log; K thresholds below 18 chunks lose again).
+    static const int min_tiles = [] { const char* e = getenv("MGLD_CONV_PAIR_MIN_TILES"); return e ? atoi(e) : 16; }();
+    static const int min_k = [] { const char* e = getenv("MGLD_CONV_PAIR_MIN_K"); return e ? atoi(e) : 18; }();
+    const bool big = p.tiles_m >= min_tiles && ntaps * p.kchunks >= min_k;
     p.cta_pair = (p.tiles_m >= 2 && (pm == 1 || (pm < 0 && big))) ? 1 : 0;
   }
   const int workers = p.cta_pair ? sms / 2 : sms;
