@@ -515,13 +515,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tmem_ld_x32(trow + 64 + c0, reinterpret_cast<uint32_t*>(g));
               tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) { v[i] += bias_s[c0 + i]; g[i] += bias_s[64 + c0 + i]; }
+              for (int i = 0; i < 32; i += 4) {   // 16-byte shared loads of the two bias slices, packed adds
+                const float4 bv = *reinterpret_cast<const float4*>(bias_s + c0 + i);
+                const float4 bg = *reinterpret_cast<const float4*>(bias_s + 64 + c0 + i);
+                fadd2(v[i], v[i + 1], v[i], v[i + 1], bv.x, bv.y);
+                fadd2(v[i + 2], v[i + 3], v[i + 2], v[i + 3], bv.z, bv.w);
+                fadd2(g[i], g[i + 1], g[i], g[i + 1], bg.x, bg.y);
+                fadd2(g[i + 2], g[i + 3], g[i + 2], g[i + 3], bg.z, bg.w);
+              }
 #pragma unroll
               for (int i = 0; i < 32; i += 2) {   // value * gelu(gate)
                 float g0, g1;
                 gelu_poly2(g0, g1, g[i], g[i + 1]);
-                v[i] *= g0;
-                v[i + 1] *= g1;
+                fmul2(v[i], v[i + 1], v[i], v[i + 1], g0, g1);
               }
               if (has_res) {
                 float r[32];

@@ -335,8 +335,9 @@ __device__ __forceinline__ void gelu_poly2(float& y0, float& y1, float x0, float
   ffma2(r0, r1, t0, t1, c[10], c[10], c[9], c[9]);
 #pragma unroll
   for (int k = 8; k >= 0; --k) ffma2(r0, r1, r0, r1, t0, t1, c[k], c[k]);
-  y0 = x0 * __saturatef(fmaf(a0, r0, 0.5f));
-  y1 = x1 * __saturatef(fmaf(a1, r1, 0.5f));
+  float p0, p1;
+  ffma2(p0, p1, a0, a1, r0, r1, 0.5f, 0.5f);
+  fmul2(y0, y1, x0, x1, __saturatef(p0), __saturatef(p1));
 }
 
 // ------------------------------------------------------------------------------------------------
