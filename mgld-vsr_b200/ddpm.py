@@ -94,19 +94,28 @@ def extract_into_tensor(a, t, x_shape):
 
 
 class _EpsRunner:
-    """struct-cond encoder + UNet on one latent tile, captured in a CUDA graph per tile shape."""
+    """struct-cond encoder + UNet on one latent tile, captured in a CUDA graph per tile shape.
+
+    Pipelined mode (single-tile canvases, `t_next` known): the struct-cond encoder only depends on (LR latent, t), not on
+    x_t, so the features of step i-1 are computed by a second branch of step i's graph, concurrently with the UNet of step
+    i (ping-pong feature buffers, two graphs).  The work per step is unchanged; the encoder's ~40 kernels fill the SMs that
+    the UNet's kernels leave idle at their tails."""
 
     def __init__(self, model, use_graph=True):
         self.m, self.use_graph = model, use_graph
         self.graphs = {}
+        self.pipes = {}
 
     def _eager(self, x, sc, t, context):
         feats = self.m.structcond_stage_model(sc, t)
         return self.m.model.diffusion_model(x, t, context=context, struct_cond=feats)
 
-    def __call__(self, x, sc, t, context):
+    def __call__(self, x, sc, t, context, t_host=None, t_next_host=None):
         if not (self.use_graph and x.is_cuda):
             return self._eager(x, sc, t, context)
+        if t_host is not None and getattr(self.m, "pipeline_struct_encoder", False) \
+                and hasattr(self.m.ops, "stats_pool_hold"):
+            return self._pipelined(x, sc, context, int(t_host), None if t_next_host is None else int(t_next_host))
         key = (tuple(x.shape), context.data_ptr(), context._version)
         g = self.graphs.get(key)
         if g is None:
@@ -128,6 +137,61 @@ class _EpsRunner:
         graph.replay()
         self.m.ops.LAUNCHES[0] += n_kernels          # kernels replayed by the graph
         return out.clone()
+
+    def _pipelined(self, x, sc, context, t_host, t_next_host):
+        ops, m = self.m.ops, self.m
+        se, unet = m.structcond_stage_model, m.model.diffusion_model
+        key = (tuple(x.shape), context.data_ptr(), context._version)
+        P = self.pipes.get(key)
+        if P is None:
+            sx, ssc = x.clone(), sc.clone()
+            st = torch.zeros(1, device=x.device, dtype=torch.long)
+            stn = torch.zeros(1, device=x.device, dtype=torch.long)
+            unet.kvc.get(ops, context)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):                                       # warm-up (lazy init, allocator)
+                    feats = se(ssc, st)
+                    unet(sx, st, context=context, struct_cond=feats)
+                F = [{k: torch.empty_like(v).copy_(v) for k, v in feats.items()} for _ in range(2)]   # ping-pong buffers
+            torch.cuda.current_stream().wait_stream(side)
+            graphs, outs, counts = [], [], []
+            for b in range(2):
+                graph = torch.cuda.CUDAGraph()
+                n0 = ops.LAUNCHES[0]
+                with torch.cuda.graph(graph):
+                    ops.stats_pool_hold(True)                           # one reset for both branches
+                    try:
+                        branch = torch.cuda.Stream()
+                        branch.wait_stream(torch.cuda.current_stream())               # fork
+                        with torch.cuda.stream(branch):
+                            fn = se(ssc, stn)                                         # features of the NEXT step ...
+                            for k_, v in fn.items():
+                                F[1 - b][k_].copy_(v)                                 # ... into the other buffer
+                        out = unet(sx, st, context=context, struct_cond=F[b])         # this step, concurrently
+                        torch.cuda.current_stream().wait_stream(branch)               # join
+                    finally:
+                        ops.stats_pool_hold(False)
+                graphs.append(graph); outs.append(out); counts.append(ops.LAUNCHES[0] - n0)
+            P = self.pipes[key] = dict(graphs=graphs, outs=outs, counts=counts, sx=sx, ssc=ssc, st=st, stn=stn, F=F,
+                                       have=None, cur=0, sc_key=None)
+        sc_key = (sc.data_ptr(), sc._version)
+        if P["have"] != t_host or P["sc_key"] != sc_key:   # cold start (first step of a clip): this step's features, eagerly
+            P["ssc"].copy_(sc)                             # (always re-read: a new clip's tensor may reuse the address)
+            P["sc_key"] = sc_key
+            P["st"].fill_(t_host)
+            feats = se(P["ssc"], P["st"])
+            for k_, v in feats.items():
+                P["F"][P["cur"]][k_].copy_(v)
+        cur = P["cur"]
+        P["sx"].copy_(x)
+        P["st"].fill_(t_host)
+        P["stn"].fill_(t_host if t_next_host is None else t_next_host)
+        P["graphs"][cur].replay()
+        ops.LAUNCHES[0] += P["counts"][cur]
+        P["have"], P["cur"] = (t_host if t_next_host is None else t_next_host), 1 - cur
+        return P["outs"][cur].clone()
 
 
 class LatentDiffusionVSRTextWT(_ModuleBase):
@@ -163,6 +227,9 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
         self.ori_timesteps = None
         self._eps = _EpsRunner(self, use_graph=use_cuda_graph)
         self.unet_clips_per_call = 2      # clips (num_frames each) batched through one struct-encoder + UNet evaluation
+        # struct encoder of step i-1 as a concurrent graph branch of step i (_EpsRunner._pipelined).  Correct (tests) but
+        # measured neutral on a power-capped B200 (DDPM loop 772 -> 769 ms, profiles/r01_dev_run42*): off by default.
+        self.pipeline_struct_encoder = False
 
     # ---- weights (script :91-108: torch.load(ckpt)["state_dict"], strict=False) ---------------------------------------
     def load_state_dict(self, sd, strict=False):
@@ -363,7 +430,7 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
         one = torch.randn((x.shape[0] // num_clips,) + tuple(x.shape[1:]), device=x.device)
         return one.repeat(num_clips, 1, 1, 1)
 
-    def _eps_tiles(self, x, struct_cond, t_in, context, offsets, tile_size, num_clips):
+    def _eps_tiles(self, x, struct_cond, t_in, context, offsets, tile_size, num_clips, t_host=None, t_next_host=None):
         """eps of every UNet tile.  Tiles (and the clips inside x) are independent UNet evaluations, so up to
         `unet_clips_per_call` clips' worth of frames go through the struct encoder + UNet as one `(b t)` batch: the
         16x16 / 8x8 levels have too few GEMM rows per clip to fill 148 SMs."""
@@ -373,7 +440,9 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
         whole_clips = nf is not None and x.shape[0] == num_clips * nf      # the temporal layers split `(b t)` by num_frames
         assert num_clips == 1 or whole_clips, "num_clips > 1 needs clips of exactly num_frames frames"
         per_call = max(1, int(self.unet_clips_per_call) // num_clips) if whole_clips else 1
-        if per_call == 1 or len(tiles) == 1:
+        if len(tiles) == 1:      # one UNet evaluation per step: the struct encoder can be pipelined across steps
+            return [self._eps(tiles[0][0], tiles[0][1], t_in[:1], context, t_host=t_host, t_next_host=t_next_host)]
+        if per_call == 1:
             return [self._eps(xt, ct, t_in[:1], context) for xt, ct in tiles]
         out = []
         for g in range(0, len(tiles), per_call):
@@ -387,7 +456,7 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
                         clip_denoised=False, repeat_noise=False, return_codebook_ids=False, quantize_denoised=False,
                         return_x0=False, temperature=1.0, noise_dropout=0.0, score_corrector=None,
                         corrector_kwargs=None, t_replace=None, tile_size=64, tile_overlap=32, batch_size=4,
-                        tile_weights=None, _step=None, num_clips=1):
+                        tile_weights=None, _step=None, num_clips=1, _t_hosts=None):
         assert tile_weights is not None
         assert not (clip_denoised or quantize_denoised or return_codebook_ids or return_x0 or repeat_noise) \
             and lr_images is None and score_corrector is None and noise_dropout == 0.0 and temperature == 1.0, \
@@ -397,7 +466,8 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
         context = self._context(c)
         _, _, h, w = x.shape
         offsets = self._tile_offsets(h, w, tile_size, tile_overlap)
-        eps_tiles = self._eps_tiles(x, struct_cond, t_in, context, offsets, tile_size, num_clips)
+        th, tn = _t_hosts if _t_hosts is not None else (None, None)   # host copies of this / the next step's timestep
+        eps_tiles = self._eps_tiles(x, struct_cond, t_in, context, offsets, tile_size, num_clips, t_host=th, t_next_host=tn)
         noise = self._step_noise(x, num_clips)                        # noise_like, util.py:265-268
         latents = self._posterior_step(x, eps_tiles, offsets, tile_size, tile_weights[0, 0].contiguous(), i, noise)
         if flows is not None:
@@ -425,11 +495,14 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
             t_replace = None
             if not (time_replace is None or time_replace == 1000):
                 t_replace = torch.full((batch_size,), self.ori_timesteps[i], device=device, dtype=torch.long)
+            replaced = not (time_replace is None or time_replace == 1000)
+            t_of = (lambda k: self.ori_timesteps[k]) if replaced else (lambda k: k)
             img = self.p_sample_canvas(img, cond, struct_cond, ts, guidance_scale=guidance_scale, lr_images=lr_images,
                                        flows=flows, masks=masks, clip_denoised=self.clip_denoised,
                                        quantize_denoised=quantize_denoised, t_replace=t_replace, tile_size=tile_size,
                                        tile_overlap=tile_overlap, batch_size=batch_size, tile_weights=tile_weights,
-                                       _step=i, num_clips=num_clips)
+                                       _step=i, num_clips=num_clips,
+                                       _t_hosts=(t_of(i), t_of(i - 1) if i > 0 else None))
             if i % log_every_t == 0 or i == timesteps - 1:
                 intermediates.append(img)
             if callback:

@@ -256,7 +256,11 @@ class _SumsPool:
     def __init__(self):
         self.bufs = {}   # key -> [buffer, next index, dirty flags]
 
+    hold = False   # while set, reset() is a no-op: several forwards captured as concurrent graph branches share one reset
+
     def reset(self):
+        if self.hold:
+            return
         for ent in self.bufs.values():
             if any(ent[2]):
                 ent[0].zero_()
@@ -288,6 +292,15 @@ _sums_pool = _SumsPool()
 def stats_pool_reset():
     """call at the start of a model forward (inside any CUDA-graph capture of it)"""
     _sums_pool.reset()
+
+
+def stats_pool_hold(on):
+    """hold(True): reset now, then ignore the resets of the forwards that follow (they may run as concurrent branches of
+    one CUDA graph and must not zero or re-hand-out each other's slots); hold(False) ends that."""
+    if on:
+        _sums_pool.hold = False
+        _sums_pool.reset()
+    _sums_pool.hold = bool(on)
 
 
 def gn_stats(x1, x2=None, groups=32):

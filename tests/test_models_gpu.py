@@ -208,3 +208,29 @@ def test_sample_canvas_num_clips_equals_clip_by_clip(use_graph):
         torch.manual_seed(7)
         one = m.sample_canvas(struct_cond=lat, x_T=x_T, flows=(ff, fb), masks=(fo, bo), **kw)
         assert rel_err(got_g[k * T:(k + 1) * T], one) < 2.5e-2
+
+
+@pytest.mark.parametrize("num_clips", [1, 2])
+def test_pipelined_struct_encoder_equals_eager(num_clips):
+    """Single-tile canvases run the struct-cond encoder of the NEXT step as a concurrent branch of the current step's CUDA
+    graph (ddpm._EpsRunner._pipelined, ping-pong feature buffers).  Same kernels, same inputs: the samples must equal the
+    eager (no graph) run up to the fp32 atomic ordering of the GroupNorm sums, over several steps and two clips in a row."""
+    m_graph, _ = build_tiny_ldm(True)
+    m_eager, _ = build_tiny_ldm(False)
+    S = 4
+    ctx = det_tensor("ctx", (1, 77, 128)).to(DEV)
+    for m in (m_graph, m_eager):
+        m.respace(S)
+    m_graph.pipeline_struct_encoder = True                  # off by default (measured neutral)
+    for clip in range(2):                                   # second clip: cold start with new conditioning
+        lat = det_tensor(f"plat{clip}", (num_clips * T, 4, 32, 32)).to(DEV)
+        x_T = det_tensor(f"pxT{clip}", (num_clips * T, 4, 32, 32)).to(DEV)
+        outs = []
+        for m in (m_graph, m_eager):
+            torch.manual_seed(11)
+            outs.append(m.sample_canvas(cond=ctx, struct_cond=lat, batch_size=T, timesteps=S, time_replace=S, x_T=x_T,
+                                        tile_size=32, tile_overlap=16, batch_size_sample=1,
+                                        **({"num_clips": num_clips} if num_clips > 1 else {})))
+        assert torch.isfinite(outs[0]).all()
+        assert rel_err(outs[0], outs[1]) < 2e-3, (clip, rel_err(outs[0], outs[1]))
+    assert m_graph._eps.pipes, "the pipelined path was not taken"
