@@ -268,7 +268,8 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
         ac_prev = np.append(1.0, ac[:-1])
         (timesteps,) = betas.shape
         self.num_timesteps = int(timesteps)
-        self.linear_start, self.linear_end = linear_start, linear_end
+        if given_betas is None:      # a respaced (given_betas) registration must not clobber the base schedule's end points
+            self.linear_start, self.linear_end = linear_start, linear_end
         f32 = lambda a: torch.tensor(a, dtype=torch.float32, device=self.device)
         post_var = (1 - self.v_posterior) * betas * (1.0 - ac_prev) / (1.0 - ac) + self.v_posterior * betas
         self.betas, self.alphas_cumprod, self.alphas_cumprod_prev = f32(betas), f32(ac), f32(ac_prev)

@@ -154,7 +154,8 @@ class VSRPipeline:
         m, T = self.model, im_lq_pch.shape[0]
         torch.manual_seed(self.seed)                                              # seed_everything per tile (:428)
         init_latent = m.get_first_stage_encoding(m.encode_first_stage(im_lq_pch))
-        noise = torch.randn_like(init_latent)
+        # == randn_like(init_latent) of script :434 for the reference's contiguous NCHW latent, whatever our strides are
+        noise = torch.randn(init_latent.shape, device=init_latent.device, dtype=init_latent.dtype)
         t = torch.full((T,), 999, device=im_lq_pch.device, dtype=torch.long)
         x_T = m.q_sample_respace(x_start=init_latent, t=t, sqrt_alphas_cumprod=self.sqrt_ac,
                                  sqrt_one_minus_alphas_cumprod=self.sqrt_1m_ac, noise=noise)
@@ -276,24 +277,33 @@ def shard_segments(num_segments, world_size, rank):
     return [s for s in range(num_segments) if s % world_size == rank]
 
 
-def gather_clip(local_segments, num_segments, frames_per_segment, world_size, rank, group=None):
+def gather_clip(local_segments, num_segments, frames_per_segment, world_size, rank, group=None, frame_shape=None,
+                device=None):
     """Stitch the output clip across ranks with ONE all-gather (NCCL on GPUs, gloo in the CPU tests).
 
     local_segments: {segment_index: (frames_per_segment, 3, H, W) uint8} for the segments `shard_segments` gave this rank.
     Ranks own ceil(num_segments / world_size) slots (unused slots are zero padding); returns the
-    (num_segments * frames_per_segment, 3, H, W) uint8 clip in segment order on every rank."""
+    (num_segments * frames_per_segment, 3, H, W) uint8 clip in segment order on every rank.
+    EVERY rank must call this, also one that owns no segment (num_segments < world_size): such a rank passes an empty
+    dict plus `frame_shape=(3, H, W)` and `device` so that it can contribute its zero slots to the collective."""
     import torch.distributed as dist
     slots = (num_segments + world_size - 1) // world_size
-    sample = next(iter(local_segments.values()))
-    buf = torch.zeros(slots, *sample.shape, dtype=torch.uint8, device=sample.device)
+    if local_segments:
+        sample = next(iter(local_segments.values()))
+        shape, device = tuple(sample.shape), sample.device
+    else:
+        if frame_shape is None or device is None:
+            raise ValueError("a rank without segments must pass frame_shape=(3,H,W) and device to gather_clip")
+        shape = (frames_per_segment,) + tuple(frame_shape)
+    buf = torch.zeros(slots, *shape, dtype=torch.uint8, device=device)
     for s, fr in local_segments.items():
         assert s % world_size == rank
         buf[s // world_size] = fr
-    out = torch.empty(world_size * slots, *sample.shape, dtype=torch.uint8, device=sample.device)
+    out = torch.empty(world_size * slots, *shape, dtype=torch.uint8, device=device)
     if world_size > 1:
         dist.all_gather_into_tensor(out, buf, group=group)      # rank r's slots land at rows [r*slots, (r+1)*slots)
     else:
         out.copy_(buf)
-    out = out.view(world_size, slots, *sample.shape)
+    out = out.view(world_size, slots, *shape)
     segs = [out[s % world_size, s // world_size] for s in range(num_segments)]
     return torch.cat(segs, 0)

@@ -61,6 +61,19 @@ def rel_err(a, b):
     return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()
 
 
+def psnr(a, b):
+    """calculate_psnr_pt, basicsr/metrics/psnr_ssim.py:52-80, on [0,1] (n,3,h,w) tensors (crop_border 0, RGB): per-image
+    10 log10(1 / (mse + 1e-8)), averaged over the frames"""
+    mse = ((a.double() - b.double()) ** 2).mean(dim=[1, 2, 3])
+    return float((10.0 * torch.log10(1.0 / (mse + 1e-8))).mean())
+
+
+def close_frac(a, b, rtol=3e-3, atol=1e-4):
+    """fraction of elements inside the north-star tolerance |a-b| <= atol + rtol*|b| (torch.allclose's criterion)"""
+    a, b = a.float(), b.float()
+    return ((a - b).abs() <= atol + rtol * b.abs()).float().mean().item()
+
+
 def raft_state_dict(shapes):
     """deterministic RAFT weights: positive BatchNorm running_var, the duplicated norm3 / downsample.1 entries of the
     reference's state_dict kept identical (they are one module there), and a small flow head so that ten random-init

@@ -29,9 +29,7 @@ def _worker(rank, world, port, num_segments, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     mine = shard_segments(num_segments, world, rank)
     local = {s: _segment_frames(s) for s in mine}
-    if not local:
-        local = {}
-    clip = gather_clip(local, num_segments, 5, world, rank) if local else None
+    clip = gather_clip(local, num_segments, 5, world, rank, frame_shape=(3, 8, 12), device="cpu")   # every rank enters
     q.put((rank, mine, clip))
     dist.barrier()
     dist.destroy_process_group()
@@ -53,6 +51,29 @@ def test_two_rank_shard_and_gather_matches_single_process():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res[0][0] == [0, 2, 4, 6] and res[1][0] == [1, 3, 5]
+    ref = torch.cat([_segment_frames(s) for s in range(num_segments)], 0)
+    for r in range(world):
+        assert torch.equal(res[r][1], ref)
+
+
+def test_fewer_segments_than_ranks():
+    """2 segments on 3 ranks (BASELINE config 2 on more GPUs than segments): the rank without work still contributes its
+    zero slot to the collective instead of hanging the others."""
+    num_segments, world = 2, 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, num_segments, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        rank, mine, clip = q.get(timeout=120)
+        res[rank] = (mine, clip)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[2][0] == []
     ref = torch.cat([_segment_frames(s) for s in range(num_segments)], 0)
     for r in range(world):
         assert torch.equal(res[r][1], ref)

@@ -90,8 +90,40 @@ def main():
     step = -10.0 * -2.3
     torch.save({"loss": loss.detach(), "grad": g, "out": (z - step * g).detach(), "step": step, "fwd_occ": fo, "bwd_occ": bo},
                os.path.join(GOLDEN, "guidance.pt"))
+    make_pipeline_golden()
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
+
+
+def make_pipeline_golden():
+    """The reference's own inference-script segment loop (script :375-530, executed from the reference tree by
+    tests/ref_harness.py) on the tiny models: latents of every unit + the SR frames (4x4 box-averaged and one full
+    resolution crop, fp16) for the GPU box, where /root/reference does not exist."""
+    import ref_harness as H
+    from test_reference_pipeline import CASES, lr_segment
+    T, S = 2, 4
+    ctx = det_tensor("ctx", (1, 77, 128))
+    model, vq, sd, vq_sd, sa, s1 = H.build_reference_models(T, ctx, S)
+    caps, orig = [], model.sample_canvas
+
+    def cap(*a, **k):
+        out = orig(*a, **k)
+        caps.append(dict(x_T=k["x_T"].clone(), samples=out[0].clone()))
+        return out
+    model.sample_canvas = cap
+    gold = {}
+    for name, (Hh, Ww, ts, st, cf, us) in CASES.items():
+        caps.clear()
+        seg = lr_segment(name, Hh, Ww)
+        with contextlib.redirect_stderr(io.StringIO()):
+            out = H.run_script_segments(model, vq, sa, s1, [seg], S, vqgantile_size=ts, vqgantile_stride=st,
+                                        colorfix_type=cf, upsample_scale=us)
+        sr = torch.from_numpy(out[0]).permute(0, 3, 1, 2) / 255.0
+        gold[name] = dict(units=[dict(c) for c in caps], sr_pool4=F.avg_pool2d(sr, 4).half(),
+                          sr_crop=sr[:, :, 192:320, 224:352].half(), sr_mean=sr.mean(dim=(2, 3)), ddpm_steps=S,
+                          psnr_vs_input=float((10 * torch.log10(1 / (((sr - (seg.clamp(-1, 1) + 1) / 2).double() ** 2)
+                                                                      .mean(dim=[1, 2, 3]) + 1e-8))).mean()))
+    torch.save(gold, os.path.join(GOLDEN, "pipeline.pt"))
 
 
 if __name__ == "__main__":
