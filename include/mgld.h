@@ -22,10 +22,11 @@
 extern "C" {
 #endif
 
-#define MGLD_ABI_VERSION 1
+#define MGLD_ABI_VERSION 2
 
 int mgld_abi_version(void);
-/* Initialise per-device state (driver entry points, shared-memory opt-in).  Must be called once per process. */
+/* Initialise per-device state (driver entry points, shared-memory opt-in).  Must be called once per process; the process
+ * is then bound to `device` (one process per GPU, as under torchrun): a later call with another device returns an error. */
 int mgld_init(int device);
 const char* mgld_last_error(void);
 
@@ -139,11 +140,12 @@ int mgld_fb_consistency_f32(const float* fwd_flow, const float* bwd_flow, float*
                             int w, float alpha, float beta, void* stream);
 /* ddpm.py:3538 compute_temporal_condition_v4 + the update of ddpm.py:4429-4435 in one call:
  *   out = latents - step * d(loss_b + loss_f)/d(latents),   step = guidance_scale * model_log_variance.
- * latents (t,c,h,w); flows (t-1,2,h,w); occlusion masks (t-1,h,w); grad_ws: t*c*h*w floats of workspace;
- * loss (optional, 1 float) receives loss_b + loss_f.                                                                 */
+ * latents (t,c,h,w); flows (t-1,2,h,w); occlusion masks (t-1,h,w); grad_ws: 8*(t*c*h*w + 1) bytes of 8-byte aligned
+ * workspace (64-bit fixed-point sums: the result is bitwise repeatable); grad_out (optional, t*c*h*w floats) receives
+ * the gradient, loss (optional, 1 float) loss_b + loss_f.                                                            */
 int mgld_motion_guidance_f32(const float* latents, const float* flow_fwd_prop, const float* flow_bwd_prop,
-                             const float* fwd_occ, const float* bwd_occ, float* grad_ws, float* out, float* loss,
-                             float step, int t, int c, int h, int w, void* stream);
+                             const float* fwd_occ, const float* bwd_occ, void* grad_ws, float* out, float* grad_out,
+                             float* loss, float step, int t, int c, int h, int w, void* stream);
 /* basicsr/archs/arch_util.py:235 resize_flow (bilinear, align_corners=False, values scaled by the size ratio)        */
 int mgld_resize_flow_f32(const float* flow, float* out, int n, int h, int w, int oh, int ow, void* stream);
 /* ddpm.py:4275-4316 + 4404-4417: Gaussian-weighted stitch of eps tiles, x0, posterior mean, noise add.

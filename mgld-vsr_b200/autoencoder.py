@@ -162,8 +162,8 @@ def encoder_shapes(dd, p="encoder."):
 
 
 class AutoencoderKL(_ModuleBase):
-    """ldm/models/autoencoder.py:299.  Only the encoder side is on the hot path (``encode``); ``decode`` of the plain
-    image VAE is used by the reference for logging only and is not implemented."""
+    """ldm/models/autoencoder.py:299.  ``encode`` is on the hot path (LR clip -> latent); ``decode`` (:361, reached through
+    ``LatentDiffusionVSRTextWT.decode_first_stage``, ddpm.py:3786) is the plain image decoder on the same kernels."""
 
     def __init__(self, ddconfig, lossconfig=None, embed_dim=4, ckpt_path=None, ignore_keys=(), image_key="image",
                  colorize_nlabels=None, monitor=None, ops=None, **ignored):
@@ -172,22 +172,39 @@ class AutoencoderKL(_ModuleBase):
         self.pool = StatsPool()
         self.loaded = False
 
-    def expected_shapes(self):
+    def expected_shapes(self, with_decoder=True):
         sh = encoder_shapes(self.dd)
         z = self.dd["z_channels"]
         sh["quant_conv.weight"], sh["quant_conv.bias"] = (2 * self.embed_dim, 2 * z, 1, 1), (2 * self.embed_dim,)
+        if with_decoder:
+            sh.update(decoder_shapes(self.dd, video=False))
+            sh["post_quant_conv.weight"], sh["post_quant_conv.bias"] = (z, self.embed_dim, 1, 1), (z,)
         return sh
 
     def load_state_dict(self, sd, strict=True, device="cuda"):
+        """The decoder half is optional (an encoder-only state_dict keeps working; ``decode`` then raises)."""
         P = _Packed(sd, torch.device(device))
         self.encoder = _Encoder(P, "encoder.", self.dd)
         self.qw, self.qb = P.f32("quant_conv.weight"), P.f32("quant_conv.bias")
+        has_dec = "decoder.conv_in.weight" in sd
+        self.decoder = _VideoDecoder(P, "decoder.", self.dd, video=False) if has_dec else None
+        if has_dec:
+            self.pqw, self.pqb = P.f32("post_quant_conv.weight"), P.f32("post_quant_conv.bias")
         self.loaded = True
-        missing = [k for k in self.expected_shapes() if k not in sd]
+        missing = [k for k in self.expected_shapes(with_decoder=has_dec) if k not in sd]
         unexpected = [k for k in sd if k not in P.used]
         if strict and missing:
             raise KeyError(f"state_dict is missing {missing[:5]}...")
         return missing, unexpected
+
+    def decode(self, z):
+        """autoencoder.py:361-364 -> (N,3,H,W) fp32"""
+        if getattr(self, "decoder", None) is None:
+            raise RuntimeError("AutoencoderKL.decode: the loaded state_dict has no decoder.* / post_quant_conv.* weights")
+        self.pool.reset(z.shape[0], z.device)
+        self.ops.stats_pool_reset()
+        z = self.ops.conv_small_f32(z.float().contiguous(), self.pqw, self.pqb)
+        return self.decoder(self.ops, z, None, pool=self.pool)
 
     def encode(self, x, return_encfea=False):
         """autoencoder.py:347-353"""
@@ -249,22 +266,25 @@ class _FuseBlock:
 
 
 class _VideoDecoder:
-    """VideoDecoder_Mix, model.py:926-1056."""
+    """VideoDecoder_Mix, model.py:926-1056; with video=False the plain image Decoder, model.py:575-684 (same topology
+    without the SpatialTemporalConv after every ResnetBlock and without the encoder-feature fusion blocks)."""
 
-    def __init__(self, P, p, dd):
+    def __init__(self, P, p, dd, video=True):
         self.nres, self.nrb = len(dd["ch_mult"]), dd["num_res_blocks"]
         self.fusion_w = 1.0
         self.conv_in = (P.f32(p + "conv_in.weight"), P.f32(p + "conv_in.bias"))
         self.mid1, self.attn, self.mid2 = (_ResnetBlock(P, p + "mid.block_1"), _AttnBlock(P, p + "mid.attn_1"),
                                            _ResnetBlock(P, p + "mid.block_2"))
-        self.tmix = _TemporalConv(P, p + "temporal_mixing", dd["num_frames"])
+        ident = lambda ops, h, pool=None: h
+        self.tmix = _TemporalConv(P, p + "temporal_mixing", dd["num_frames"]) if video else ident
         self.up = {}
         for lvl in range(self.nres):
-            blocks = [(_ResnetBlock(P, f"{p}up.{lvl}.block.{b}"), _TemporalConv(P, f"{p}up.{lvl}.temporal_mixing.{b}", dd["num_frames"]))
+            blocks = [(_ResnetBlock(P, f"{p}up.{lvl}.block.{b}"),
+                       _TemporalConv(P, f"{p}up.{lvl}.temporal_mixing.{b}", dd["num_frames"]) if video else ident)
                       for b in range(self.nrb + 1)]
             ups = _Upsample(P, f"{p}up.{lvl}.upsample") if lvl != 0 else None
             fuse = None
-            if lvl != self.nres - 1 and lvl != 0:
+            if video and lvl != self.nres - 1 and lvl != 0:
                 fuse = _FuseBlock(P, f"{p}fusion_layer_{lvl}", dd["ch"] * dd["ch_mult"][lvl])
             self.up[lvl] = (blocks, fuse, ups)
         self.norm_out = P.norm(p + "norm_out")
@@ -288,7 +308,8 @@ class _VideoDecoder:
         return ops.conv3x3_small_cout(_gn_silu(ops, h, self.norm_out, 1e-6, True), self.wout, self.bout)
 
 
-def decoder_shapes(dd, p="decoder."):
+def decoder_shapes(dd, p="decoder.", video=True):
+    """state_dict manifest of VideoDecoder_Mix (video=True) or the plain Decoder of AutoencoderKL (video=False)"""
     sh, ch, mult, nrb = {}, dd["ch"], dd["ch_mult"], dd["num_res_blocks"]
     nres = len(mult)
     cin = ch * mult[-1]
@@ -297,12 +318,14 @@ def decoder_shapes(dd, p="decoder."):
     _shapes_resnet(sh, p + "mid.block_2", cin, cin)
 
     def tconv(q, C):
+        if not video:
+            return
         sh[q + ".temporal_conv.weight"], sh[q + ".temporal_conv.bias"], sh[q + ".temporal_alpha"] = (C, C, 3, 1, 1), (C,), (1,)
 
     tconv(p + "temporal_mixing", cin)
     for lvl in reversed(range(nres)):
         co = ch * mult[lvl]
-        if lvl != nres - 1 and lvl != 0:
+        if video and lvl != nres - 1 and lvl != 0:
             f = f"{p}fusion_layer_{lvl}"
             _shapes_resnet(sh, f + ".encode_enc_1", 2 * co, co, "conv_out")
             for i in range(2):

@@ -81,6 +81,24 @@ __device__ __forceinline__ void scatter_bilinear(float* __restrict__ g, int h, i
   if (yin1 && xin1) atomicAdd(g + (c.y0 + 1) * w + c.x0 + 1, c.se * v);
 }
 
+// Deterministic accumulation for the guidance gradient: every contribution is rounded once to a 2^-44 fixed-point
+// integer and summed with 64-bit integer atomics.  Integer addition is associative, so the sum - and with it the whole
+// DDPM trajectory - is bitwise repeatable whatever order the scheduler runs the scatter in (the fp32 atomicAdd form was
+// not: the L1 sign() and the ~460x last step amplified its rounding differences).  |contribution| <=
+// 1/(C*h*w) <= 1, at most a few dozen land on one element: no overflow; resolution 5.7e-14 << fp32 ulp of the result.
+constexpr double kFixScale = 17592186044416.0;  // 2^44
+__device__ __forceinline__ void fix_add(long long* acc, float v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(acc), (unsigned long long)__double2ll_rn((double)v * kFixScale));
+}
+__device__ __forceinline__ void scatter_bilinear_fix(long long* __restrict__ g, int h, int w, const Corner& c, float v) {
+  const bool xin0 = c.x0 >= 0 && c.x0 < w, xin1 = c.x0 + 1 >= 0 && c.x0 + 1 < w;
+  const bool yin0 = c.y0 >= 0 && c.y0 < h, yin1 = c.y0 + 1 >= 0 && c.y0 + 1 < h;
+  if (yin0 && xin0) fix_add(g + c.y0 * w + c.x0, c.nw * v);
+  if (yin0 && xin1) fix_add(g + c.y0 * w + c.x0 + 1, c.ne * v);
+  if (yin1 && xin0) fix_add(g + (c.y0 + 1) * w + c.x0, c.sw * v);
+  if (yin1 && xin1) fix_add(g + (c.y0 + 1) * w + c.x0 + 1, c.se * v);
+}
+
 __device__ __forceinline__ void load_flow(const float* __restrict__ flow, int layout, int n, int hw, int p, float* fx,
                                           float* fy) {
   if (layout == 0) {  // (n,h,w,2)
@@ -173,8 +191,8 @@ __global__ void fb_consistency_kernel(const float* __restrict__ fwd, const float
 __global__ void motion_guidance_grad_kernel(const float* __restrict__ z, const float* __restrict__ flow_fwd_prop,
                                             const float* __restrict__ flow_bwd_prop,
                                             const float* __restrict__ fwd_occ, const float* __restrict__ bwd_occ,
-                                            float* __restrict__ grad, float* __restrict__ loss, int T, int C, int H,
-                                            int W) {
+                                            long long* __restrict__ grad, long long* __restrict__ loss, int T,
+                                            int C, int H, int W) {
   const int hw = H * W;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const int term = blockIdx.y;
@@ -208,21 +226,29 @@ __global__ void motion_guidance_grad_kernel(const float* __restrict__ z, const f
       local += fabsf(d);
       const float g = m * s * invN;
       if (g != 0.f) {
-        atomicAdd(grad + (fb * C + c) * hw + p, -g);
-        if (fa >= 0) scatter_bilinear(grad + (fa * C + c) * hw, H, W, cr, g);
+        fix_add(grad + (fb * C + c) * hw + p, -g);
+        if (fa >= 0) scatter_bilinear_fix(grad + (fa * C + c) * hw, H, W, cr, g);
       }
     }
   }
   if (loss) {
     for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-    if ((threadIdx.x & 31) == 0 && local != 0.f) atomicAdd(loss, local / (float)(C * hw));
+    if ((threadIdx.x & 31) == 0 && local != 0.f) fix_add(loss, local / (float)(C * hw));
   }
 }
 
-__global__ void axpy_update_kernel(const float* __restrict__ z, const float* __restrict__ grad, float* __restrict__ out,
-                                   float step, int n) {
+// out = z - step * grad; the fixed-point sums are rounded to fp32 once here.  grad_f32 (optional) receives the gradient,
+// loss_f32 (optional) the loss; both alias the head of the workspace, which is why thread 0 converts the loss last.
+__global__ void axpy_update_kernel(const float* __restrict__ z, const long long* __restrict__ grad,
+                                   float* __restrict__ out, float* __restrict__ grad_f32, float step, int n,
+                                   const long long* __restrict__ loss_fix, float* __restrict__ loss_f32) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __fadd_rn(z[i], -__fmul_rn(step, grad[i]));
+  if (i < n) {
+    const float g = (float)((double)grad[i] * (1.0 / kFixScale));
+    out[i] = __fadd_rn(z[i], -__fmul_rn(step, g));
+    if (grad_f32) grad_f32[i] = g;
+  }
+  if (i == 0 && loss_f32) *loss_f32 = (float)((double)*loss_fix * (1.0 / kFixScale));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -325,21 +351,23 @@ extern "C" int mgld_fb_consistency_f32(const float* fwd_flow, const float* bwd_f
 }
 
 extern "C" int mgld_motion_guidance_f32(const float* latents, const float* flow_fwd_prop, const float* flow_bwd_prop,
-                                        const float* fwd_occ, const float* bwd_occ, float* grad_ws, float* out,
-                                        float* loss, float step, int t, int c, int h, int w, void* stream) {
+                                        const float* fwd_occ, const float* bwd_occ, void* grad_ws, float* out,
+                                        float* grad_out, float* loss, float step, int t, int c, int h, int w,
+                                        void* stream) {
   MGLD_CHECK_ARG(latents && grad_ws && out && t >= 1 && c > 0 && h > 0 && w > 0, "motion_guidance: bad arguments");
   MGLD_CHECK_ARG(t == 1 || (flow_fwd_prop && flow_bwd_prop && fwd_occ && bwd_occ), "motion_guidance: null flows");
+  MGLD_CHECK_ARG((reinterpret_cast<uintptr_t>(grad_ws) & 7) == 0, "motion_guidance: workspace must be 8-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   const int n = t * c * h * w;
-  MGLD_CUDA(cudaMemsetAsync(grad_ws, 0, sizeof(float) * (size_t)n, s));
-  if (loss) MGLD_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
+  long long* acc = static_cast<long long*>(grad_ws);          // n gradient sums + 1 loss sum, 2^-44 fixed point
+  MGLD_CUDA(cudaMemsetAsync(acc, 0, sizeof(long long) * ((size_t)n + 1), s));
   if (t >= 2) {
     motion_guidance_grad_kernel<<<pix_grid(h * w, 2 * (t - 1)), 256, 0, s>>>(latents, flow_fwd_prop, flow_bwd_prop,
-                                                                              fwd_occ, bwd_occ, grad_ws, loss, t, c,
-                                                                              h, w);
+                                                                              fwd_occ, bwd_occ, acc, loss ? acc + n : nullptr,
+                                                                              t, c, h, w);
     MGLD_LAUNCH_CHECK("motion_guidance_grad_kernel");
   }
-  axpy_update_kernel<<<(n + 255) / 256, 256, 0, s>>>(latents, grad_ws, out, step, n);
+  axpy_update_kernel<<<(n + 255) / 256, 256, 0, s>>>(latents, acc, out, grad_out, step, n, acc + n, loss);
   MGLD_LAUNCH_CHECK("axpy_update_kernel");
   return MGLD_OK;
 }

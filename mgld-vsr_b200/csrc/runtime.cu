@@ -11,6 +11,7 @@ static thread_local char g_err[512] = "";
 static EncodeTiledFn g_encode = nullptr;
 static int g_num_sms = 0;
 static bool g_init = false;
+static int g_device = -1;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -96,6 +97,14 @@ extern "C" int mgld_abi_version(void) { return MGLD_ABI_VERSION; }
 extern "C" const char* mgld_last_error(void) { return g_err; }
 
 extern "C" int mgld_init(int device) {
+  // One process drives one GPU (one rank per GPU under torchrun): the shared-memory opt-ins, the co-resident cluster count
+  // and the SM count are cached per process, so a second device in the same process is refused instead of silently
+  // running with the first device's capabilities.
+  if (g_init && device != g_device) {
+    set_error("mgld_init(%d): this process is already bound to device %d (libmgld is one-process-per-GPU)", device, g_device);
+    return MGLD_ERR_ARG;
+  }
+  if (g_init) return MGLD_OK;
   MGLD_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
   MGLD_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -112,6 +121,7 @@ extern "C" int mgld_init(int device) {
     return MGLD_ERR_CUDA;
   }
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  g_device = device;
   g_init = true;
   return MGLD_OK;
 }

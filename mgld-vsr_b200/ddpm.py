@@ -116,7 +116,7 @@ class _EpsRunner:
         if t_host is not None and getattr(self.m, "pipeline_struct_encoder", False) \
                 and hasattr(self.m.ops, "stats_pool_hold"):
             return self._pipelined(x, sc, context, int(t_host), None if t_next_host is None else int(t_next_host))
-        key = (tuple(x.shape), context.data_ptr(), context._version)
+        key = (tuple(x.shape), id(context), context._version)
         g = self.graphs.get(key)
         if g is None:
             sx, ssc, st = x.clone(), sc.clone(), t.clone()
@@ -131,8 +131,8 @@ class _EpsRunner:
             n0 = self.m.ops.LAUNCHES[0]
             with torch.cuda.graph(graph):
                 out = self._eager(sx, ssc, st, context)
-            g = self.graphs[key] = (graph, sx, ssc, st, out, self.m.ops.LAUNCHES[0] - n0)
-        graph, sx, ssc, st, out, n_kernels = g
+            g = self.graphs[key] = (graph, sx, ssc, st, out, self.m.ops.LAUNCHES[0] - n0, context)   # context kept alive: id() stays unique
+        graph, sx, ssc, st, out, n_kernels, _ = g
         sx.copy_(x); ssc.copy_(sc); st.copy_(t)
         graph.replay()
         self.m.ops.LAUNCHES[0] += n_kernels          # kernels replayed by the graph
@@ -141,7 +141,7 @@ class _EpsRunner:
     def _pipelined(self, x, sc, context, t_host, t_next_host):
         ops, m = self.m.ops, self.m
         se, unet = m.structcond_stage_model, m.model.diffusion_model
-        key = (tuple(x.shape), context.data_ptr(), context._version)
+        key = (tuple(x.shape), id(context), context._version)
         P = self.pipes.get(key)
         if P is None:
             sx, ssc = x.clone(), sc.clone()
@@ -175,7 +175,7 @@ class _EpsRunner:
                         ops.stats_pool_hold(False)
                 graphs.append(graph); outs.append(out); counts.append(ops.LAUNCHES[0] - n0)
             P = self.pipes[key] = dict(graphs=graphs, outs=outs, counts=counts, sx=sx, ssc=ssc, st=st, stn=stn, F=F,
-                                       have=None, cur=0, sc_key=None)
+                                       have=None, cur=0, sc_key=None, context=context)
         sc_key = (sc.data_ptr(), sc._version)
         if P["have"] != t_host or P["sc_key"] != sc_key:   # cold start (first step of a clip): this step's features, eagerly
             P["ssc"].copy_(sc)                             # (always re-read: a new clip's tensor may reuse the address)
@@ -237,6 +237,9 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
             return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
         dev = str(self.device)
         missing, unexpected = [], []
+        # captured graphs replay against the weight tensors they were captured with: new weights invalidate them
+        self._eps.graphs.clear()
+        self._eps.pipes.clear()
         for prefix, mod in (("model.diffusion_model.", self.model.diffusion_model),
                             ("first_stage_model.", self.first_stage_model),
                             ("structcond_stage_model.", self.structcond_stage_model),
@@ -326,10 +329,11 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
         return self.scale_factor * z
 
     def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):
-        """ddpm.py:3786 — image VAE decode (used by the reference for logging; the VSR output goes through
-        VideoAutoencoderKLResi.decode instead)."""
-        if not hasattr(self.first_stage_model, "decode"):
-            raise NotImplementedError("AutoencoderKL.decode is not on the VSR inference path")
+        """ddpm.py:3786-3840 (no split_input_params, KL first stage): AutoencoderKL.decode(z / scale_factor).  The VSR
+        scripts decode through VideoAutoencoderKLResi.decode instead; this is the image-VAE path (`x_samples =
+        model.decode_first_stage(samples)`, commented alternative at script :467)."""
+        if predict_cids or force_not_quantize:
+            raise NotImplementedError("VQ first stages (predict_cids / force_not_quantize) are not part of the VSR path")
         return self.first_stage_model.decode(1.0 / self.scale_factor * z)
 
     def get_learned_conditioning(self, c):
@@ -393,11 +397,20 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
         return out
 
     def _context(self, cond):
+        """cross-attention context of a `cond` in any of the reference's forms (tensor, list, {'c_crossattn': [...]}).  The
+        concatenation of a list is cached on the identity + version of its parts, so that every DDPM step sees the SAME
+        tensor object (the K/V cache and the captured graphs are keyed on it)."""
         if isinstance(cond, dict):
-            return torch.cat(cond["c_crossattn"], 1)
-        if isinstance(cond, list):
-            return torch.cat(cond, 1)
-        return cond
+            cond = cond["c_crossattn"]
+        if not isinstance(cond, (list, tuple)):
+            return cond
+        if len(cond) == 1:
+            return cond[0]
+        key = tuple((id(c), c._version) for c in cond)
+        hit = getattr(self, "_ctx_cat", None)
+        if hit is None or hit[0] != key:
+            hit = self._ctx_cat = (key, torch.cat(list(cond), 1), list(cond))
+        return hit[1]
 
     def _posterior_step(self, x, eps_tiles, offsets, tile_size, tile_w, i, noise):
         h = self._h

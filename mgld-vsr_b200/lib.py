@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("MGLD_LIB") or os.path.join(_HERE, "libmgld.so")   # M
 
 _lib = None
 _inited = set()
+ABI_VERSION = 2     # include/mgld.h MGLD_ABI_VERSION
 
 
 class MgldError(RuntimeError):
@@ -52,6 +53,8 @@ def load():
     lib = ctypes.CDLL(LIB_PATH)
     lib.mgld_last_error.restype = ctypes.c_char_p
     lib.mgld_abi_version.restype = ctypes.c_int
+    if lib.mgld_abi_version() != ABI_VERSION:
+        raise MgldError(f"{LIB_PATH} has ABI version {lib.mgld_abi_version()}, this package expects {ABI_VERSION}: rebuild it")
     lib.mgld_conv_gemm_workspace_bytes.restype = ctypes.c_longlong
     _lib = lib
     return lib

@@ -188,15 +188,16 @@ def motion_guidance_f32(latents, flow_fwd_prop, flow_bwd_prop, fwd_occ, bwd_occ,
     """latents (t,c,h,w); flows (t-1,2,h,w); occs (t-1,h,w).  Returns latents - step * grad (and the loss)."""
     latents = _f32c(latents)
     t, c, h, w = latents.shape
-    ws = torch.empty_like(latents)
+    ws = torch.empty(latents.numel() + 1, device=latents.device, dtype=torch.int64)   # fixed-point sums (deterministic)
     out = torch.empty_like(latents)
     loss = torch.empty(1, device=latents.device, dtype=torch.float32) if want_loss else None
+    grad = torch.empty_like(latents) if want_loss else None
     args = [_f32c(a) if a is not None else None for a in (flow_fwd_prop, flow_bwd_prop, fwd_occ, bwd_occ)]
     _count(2)
     _L.check(_L.lib().mgld_motion_guidance_f32(_L.ptr(latents), _L.ptr(args[0]), _L.ptr(args[1]), _L.ptr(args[2]),
-                                               _L.ptr(args[3]), _L.ptr(ws), _L.ptr(out), _L.ptr(loss),
+                                               _L.ptr(args[3]), _L.ptr(ws), _L.ptr(out), _L.ptr(grad), _L.ptr(loss),
                                                ctypes.c_float(step), t, c, h, w, _L.stream_ptr()))
-    return (out, loss, ws) if want_loss else out
+    return (out, loss, grad) if want_loss else out
 
 
 def resize_flow_f32(flow, oh, ow):

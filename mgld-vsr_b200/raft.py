@@ -168,6 +168,7 @@ class RAFT_SR(_ModuleBase):
     def load_state_dict(self, sd, strict=True, device="cuda"):
         sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}     # raft_arch.py:700-703
         dev = torch.device(device)
+        self.__dict__.pop("_graphed", None)        # a captured graph replays against the old weight tensors
         missing = [k for k in self.expected_shapes() if k not in sd]
         if strict and missing:
             raise KeyError(f"state_dict is missing {missing[:5]}...")

@@ -227,12 +227,12 @@ class _KVCache:
         self.ws = None
 
     def get(self, ops, context):
-        key = (context.data_ptr(), context._version, tuple(context.shape))
-        if self.key != key:
+        # keyed on the tensor OBJECT (kept alive here, so its address cannot be recycled by another tensor) + its version
+        if self.key is None or self.key[0] is not context or self.key[1] != context._version:
             assert context.shape[0] == 1, "one text context per clip (SURVEY.md D4/D6)"
             ctx = context[0].to(self.w.device, torch.float16).contiguous()
             self.kv = ops.conv_gemm(ctx, self.w)          # [ctx_len, sum 2C]
-            self.key = key
+            self.key = (context, context._version)
         return self.kv
 
 

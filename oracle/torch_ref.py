@@ -383,6 +383,28 @@ def video_decoder_forward(sd, ddcfg, z, enc_fea, fusion_w=1.0, prefix="decoder."
     return _conv(sd, "conv_out", _swish(_gn6(sd, "norm_out", h)))
 
 
+def decoder_forward(sd, ddcfg, z, prefix="decoder."):
+    """Decoder.forward (plain image decoder of AutoencoderKL), model.py:648-684."""
+    sd = _strip(sd, prefix)
+    nres, nrb = len(ddcfg["ch_mult"]), ddcfg["num_res_blocks"]
+    h = _conv(sd, "conv_in", z)
+    h = vae_resnet_block(sd, "mid.block_1", h)
+    h = vae_attn_block(sd, "mid.attn_1", h)
+    h = vae_resnet_block(sd, "mid.block_2", h)
+    for lvl in reversed(range(nres)):
+        for b in range(nrb + 1):
+            h = vae_resnet_block(sd, f"up.{lvl}.block.{b}", h)
+        if lvl != 0:
+            h = _conv(sd, f"up.{lvl}.upsample.conv", F.interpolate(h, scale_factor=2.0, mode="nearest"))
+    return _conv(sd, "conv_out", _swish(_gn6(sd, "norm_out", h)))
+
+
+def autoencoder_kl_decode(sd, ddcfg, z, prefix="first_stage_model."):
+    """AutoencoderKL.decode, autoencoder.py:361-364"""
+    z = F.conv2d(z, sd[prefix + "post_quant_conv.weight"], sd[prefix + "post_quant_conv.bias"])
+    return decoder_forward(sd, ddcfg, z, prefix + "decoder.")
+
+
 def video_vae_encode(sd, ddcfg, x):
     """VideoAutoencoderKLResi.encode, autoencoder.py:1674-1679 -> (moments, enc_fea)"""
     h, fea = vae_encoder_forward(sd, ddcfg, x, "encoder.", return_fea=True)

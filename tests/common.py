@@ -1,4 +1,5 @@
 """Shared test helpers: deterministic weights keyed by parameter name, tiny configs, synthetic inputs."""
+import contextlib
 import hashlib
 import os
 import sys
@@ -72,6 +73,43 @@ def close_frac(a, b, rtol=3e-3, atol=1e-4):
     """fraction of elements inside the north-star tolerance |a-b| <= atol + rtol*|b| (torch.allclose's criterion)"""
     a, b = a.float(), b.float()
     return ((a - b).abs() <= atol + rtol * b.abs()).float().mean().item()
+
+
+class cpu_rng:
+    """Context manager: every `torch.randn` / `torch.randn_like` inside draws from the CPU generator and is then moved to
+    the requested device.  The reference run on the CPU (golden fixtures, oracle pipeline) and the product run on the GPU
+    then consume ONE identical noise stream — on a CUDA device the reference itself mixes a CPU draw (posterior sample,
+    distributions.py:36) with CUDA-generator draws, which no other machine could reproduce."""
+
+    def __enter__(self):
+        self._randn, self._randn_like = torch.randn, torch.randn_like
+
+        def randn(*size, device=None, dtype=None, generator=None, **kw):
+            if len(size) == 1 and not isinstance(size[0], int):
+                size = tuple(size[0])
+            out = self._randn(*size, dtype=dtype, generator=generator, **kw)
+            return out.to(device) if device is not None else out
+
+        def randn_like(x, **kw):
+            return self._randn(tuple(x.shape), dtype=x.dtype).to(x.device)
+        torch.randn, torch.randn_like = randn, randn_like
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn, torch.randn_like = self._randn, self._randn_like
+        return False
+
+
+@contextlib.contextmanager
+def fp32_reference_math():
+    """TF32 off for cuDNN convs and cuBLAS matmuls: the oracle on the GPU must be a true fp32 reference (a TF32 conv has a
+    10-bit mantissa — coarser than the fp16 path under test)"""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        yield
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
 def raft_state_dict(shapes):

@@ -23,3 +23,14 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(pytest.mark.skip(reason="no CUDA device"))
         if "reference" in item.keywords and not has_ref:
             item.add_marker(pytest.mark.skip(reason="/root/reference not present"))
+
+
+@pytest.fixture(autouse=True)
+def _fp32_oracle_on_gpu():
+    """Every GPU test compares against the oracle evaluated in TRUE fp32: TF32 is switched off for cuDNN and cuBLAS
+    (the 'fp32 oracle' of the tiny network tests ran tf32 implicit-GEMM convs)."""
+    import torch
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 25
     for s in syms:
         assert hasattr(handle, s), f"{s} declared in mgld.h but not exported by libmgld.so"
-    assert handle.mgld_abi_version() == 1
+    assert handle.mgld_abi_version() == 2
 
 
 def test_struct_mirrors_match_header_layout():

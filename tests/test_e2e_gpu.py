@@ -1,0 +1,276 @@
+"""End-to-end acceptance on the GPU (north-star: outputs within rtol 3e-3 / atol 1e-4 fp16 of the reference path, PSNR within
+0.05 dB on a fixed synthetic clip):
+
+  * `VSRPipeline` against the committed outputs of the reference's OWN inference script (tests/golden/pipeline.pt, made by
+    tools/make_golden.py from /root/reference) — untiled + AdaIN and VAE-tiled + wavelet + reflect pad;
+  * `VSRPipeline` at ddpm_steps=50 on a fixed synthetic 8-frame 128x128 clip against the oracle pipeline
+    (oracle/pipeline_ref.py, pinned to the reference script by tests/test_reference_pipeline.py) evaluated in true fp32 on
+    the same GPU with the same noise stream: |dPSNR| <= 0.05 dB;
+  * a teacher-forced 50-step check of the sampler: at every step the product gets the ORACLE's x_t, so errors cannot
+    accumulate or hide; compared element-wise with the north-star tolerance, and against the reference's deployment
+    numerics (the oracle under fp16 autocast) as the yardstick of what an fp16 path can reach;
+  * both VAEs at the real shapes (SD ch=128, T=5, 512x512 and one 736x960 VAE tile of the 720p configuration);
+  * bitwise run-to-run repeatability of `sample_canvas` (deterministic guidance scatter).
+"""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from common import (GOLDEN, TINY_DD, TINY_STRUCT, TINY_UNET, close_frac, cpu_rng, det_state_dict, det_tensor, psnr,
+                    raft_state_dict, rel_err)
+from oracle import pipeline_ref as PR
+from oracle import torch_ref as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+class DeviceRng(PR.TorchCpuRng):
+    """CPU-generator draws moved to the GPU: the stream `cpu_rng()` gives the product"""
+
+    def __init__(self, seed):
+        super().__init__(seed, DEV)
+
+
+def to_dev(sd):
+    return {k: v.to(DEV) for k, v in sd.items()}
+
+
+def build_models(T, S, use_graph=True, with_raft=True):
+    from mgld_vsr_b200.autoencoder import VideoAutoencoderKLResi
+    from mgld_vsr_b200.config import _wrap
+    from mgld_vsr_b200.ddpm import LatentDiffusionVSRTextWT
+    dd = dict(TINY_DD, num_frames=T)
+    cfg = _wrap(dict(
+        first_stage_config=dict(target="ldm.models.autoencoder.AutoencoderKL",
+                                params=dict(ddconfig=dd, embed_dim=4, lossconfig=dict(target="torch.nn.Identity"))),
+        cond_stage_config=dict(target="ldm.modules.encoders.modules.FrozenOpenCLIPEmbedder", params=dict(freeze=True)),
+        structcond_stage_config=dict(target="ldm.modules.diffusionmodules.openaimodel.InflatedEncoderUNetModelWT",
+                                     params=dict(TINY_STRUCT, num_frames=T)),
+        flownet_config=dict(target="basicsr.archs.raft_arch.RAFT_SR", params=dict(model="normal", load_path=None))
+        if with_raft else None,
+        unet_config=dict(target="ldm.modules.diffusionmodules.openaimodel.InflatedUNetModelDualcondV2",
+                         params=dict(TINY_UNET, num_frames=T))))
+    m = LatentDiffusionVSRTextWT(**cfg, num_frames=T, linear_start=0.00085, linear_end=0.0120, timesteps=1000,
+                                 image_size=512, channels=4, scale_factor=0.18215, conditioning_key="crossattn",
+                                 time_replace=1000, use_cuda_graph=use_graph)
+    shapes = {}
+    for pre, mod in (("model.diffusion_model.", m.model.diffusion_model), ("first_stage_model.", m.first_stage_model),
+                     ("structcond_stage_model.", m.structcond_stage_model)):
+        shapes.update({pre + k: v for k, v in mod.expected_shapes().items()})
+    sd = det_state_dict(shapes)
+    if with_raft:
+        sd.update({"flownet_model." + k: v for k, v in raft_state_dict(m.flownet_model.expected_shapes()).items()})
+    m.load_state_dict(sd, strict=False)
+    ctx = det_tensor("ctx", (1, 77, 128)).to(DEV)
+    m.cond_stage_model.set_embedding(ctx)
+    vq = VideoAutoencoderKLResi(ddconfig=dd, embed_dim=4)
+    vq_sd = det_state_dict(vq.expected_shapes())
+    vq.load_state_dict(vq_sd)
+    m.respace(S)
+    return m, vq, to_dev(sd), to_dev(vq_sd), ctx, dd
+
+
+def robust_close(got, ref, mean_tol, frac_tol, thr=1e-2):
+    """the guidance's sign() of nearly equal latents + its ~460x last step flips isolated pixels on an
+    fp16-level difference: compare robust statistics (mean error, fraction of outliers) instead of the max"""
+    d = (got.float() - ref.float()).abs()
+    return d.mean().item() < mean_tol and (d > thr).float().mean().item() < frac_tol, \
+        (d.mean().item(), (d > thr).float().mean().item(), d.max().item())
+
+
+@pytest.mark.parametrize("name", ["untiled_adain", "tiled_wavelet_pad"])
+def test_pipeline_vs_reference_script_golden(name):
+    """product on the B200 vs the reference's own script run (fp32, CPU) recorded in tests/golden/pipeline.pt"""
+    from mgld_vsr_b200.pipeline import VSRPipeline
+    from test_reference_pipeline import CASES, T, lr_segment, seg01
+    gold = torch.load(os.path.join(GOLDEN, "pipeline.pt"))[name]
+    S = gold["ddpm_steps"]
+    Hh, Ww, ts, st, cf, us = CASES[name]
+    m, vq, sd, vq_sd, ctx, dd = build_models(T, S)
+    pipe = VSRPipeline(m, vq, ddpm_steps=S, n_frames=T, vqgantile_size=ts, vqgantile_stride=st, colorfix_type=cf, seed=42)
+    pipe.upsample_scale = us
+    seg = lr_segment(name, Hh, Ww).to(DEV)
+    caps, orig = [], m.sample_canvas
+
+    def cap(**kw):
+        out = orig(**kw)
+        caps.append((kw["x_T"], out))
+        return out
+    m.sample_canvas = cap
+    with cpu_rng():
+        sr = pipe.super_resolve_segment(seg, ctx)
+    assert sr.shape == (T, 3, Hh, Ww) and torch.isfinite(sr).all()
+    units = [(x[k * T:(k + 1) * T], o[k * T:(k + 1) * T]) for x, o in caps for k in range(o.shape[0] // T)]
+    assert len(units) == len(gold["units"])
+    for (x_T, samples), g in zip(units, gold["units"]):
+        assert rel_err(x_T.cpu(), g["x_T"]) < 3e-3                      # LR latent (VAE encoder) + the shared noise stream
+        ok, stats = robust_close(samples.cpu(), g["samples"], 2e-3, 5e-3, thr=2e-2)
+        assert ok, stats
+    ok, stats = robust_close(F.avg_pool2d(sr, 4).cpu(), gold["sr_pool4"].float(), 1e-3, 5e-3)
+    assert ok, stats
+    ok, stats = robust_close(sr[:, :, 192:320, 224:352].cpu(), gold["sr_crop"].float(), 1.5e-3, 1e-2)
+    assert ok, stats
+    assert (sr.mean(dim=(2, 3)).cpu() - gold["sr_mean"]).abs().max() < 1e-3
+    assert abs(psnr(sr, seg01(seg)) - gold["psnr_vs_input"]) < 0.05
+
+
+@pytest.mark.parametrize("flow_mode", ["raft", "synthetic"])
+def test_pipeline_e2e_psnr_50_steps(flow_mode):
+    """fixed synthetic 8-frame 128x128 clip, ddpm_steps=50, 2 segments of 4 frames, motion guidance on"""
+    from mgld_vsr_b200.pipeline import VSRPipeline
+    T, S, n = 4, 50, 8
+    m, vq, sd, vq_sd, ctx, dd = build_models(T, S)
+    g = torch.Generator().manual_seed(2024)
+    hr = F.interpolate(torch.rand(n, 3, 24, 24, generator=g), size=(512, 512), mode="bicubic").clamp(0, 1)
+    hr = (hr + 0.02 * torch.randn(n, 3, 512, 512, generator=g)).clamp(0, 1)               # the "ground truth" clip
+    lr = F.interpolate(hr, size=(128, 128), mode="bicubic", antialias=True).clamp(0, 1).to(DEV) * 2 - 1
+    pipe = VSRPipeline(m, vq, ddpm_steps=S, n_frames=T, seed=42)
+    flows = None
+    if flow_mode == "synthetic":                                                         # mixed occlusion masks
+        flows = []
+        for s_ in range(2):
+            ff = 1.5 * F.interpolate(det_tensor(f"e2e_ff{s_}", (T - 1, 2, 8, 8)), size=(64, 64), mode="bicubic").to(DEV)
+            fb = -ff + 0.2 * F.interpolate(det_tensor(f"e2e_fb{s_}", (T - 1, 2, 8, 8)), size=(64, 64), mode="bicubic").to(DEV)
+            flows.append((ff, fb))
+    with cpu_rng():
+        sr = pipe(lr, context=ctx, flows_override=flows)
+    assert sr.shape == (n, 3, 512, 512) and torch.isfinite(sr).all()
+    # oracle pipeline, fp32 on the same GPU, same noise stream (the product re-seeds per unit: so does the oracle here)
+    segs, _ = pipe.segments(lr)
+    rng = DeviceRng(42)
+    outs = []
+    with torch.no_grad():
+        for si, seg in enumerate(segs):
+            rng.seed()
+            fn = None if flows is None else (lambda _lq, si=si: None)
+            if flows is not None:
+                f0, f1 = flows[si]
+                # estimate_flows resizes RAFT output (h/4) to the latent grid: feed flows that resize to the given ones
+                fn = lambda _lq, f0=f0, f1=f1: (2.0 * F.interpolate(f0, scale_factor=2.0, mode="nearest")[None],
+                                                2.0 * F.interpolate(f1, scale_factor=2.0, mode="nearest")[None])
+            outs.append(PR.sr_segment(sd, TINY_UNET, TINY_STRUCT, dd, vq_sd, dd, seg, ctx, rng, ddpm_steps=S, flow_fn=fn))
+    ref = torch.cat(outs, 0)[:n]
+    p_got, p_ref = psnr(sr.cpu(), hr), psnr(ref.cpu(), hr)
+    print(f"[e2e {flow_mode}] PSNR vs ground truth: product {p_got:.4f} dB, oracle {p_ref:.4f} dB; product vs oracle "
+          f"{psnr(sr, ref):.2f} dB; mean |d| {(sr - ref).abs().mean().item():.2e}")
+    assert abs(p_got - p_ref) <= 0.05, (p_got, p_ref)
+    assert psnr(sr, ref) > 40.0
+    ok, stats = robust_close(sr, ref, 1.5e-3, 1e-2)
+    assert ok, stats
+
+
+def test_sampler_teacher_forced_50_steps():
+    """Every one of the 50 DDPM steps on a 2x2-tile canvas, the product fed the ORACLE's x_t (teacher forcing):
+    (a) eps stitch + posterior (no guidance): element-wise north-star tolerance rtol 3e-3 / atol 1e-4 and max error
+        relative to the latent range; yardstick = the oracle under fp16 autocast (the reference's deployment numerics);
+    (b) with motion guidance: same, robust to isolated sign flips of the L1 gradient (D8)."""
+    T, S, h, w = 2, 50, 80, 72
+    m, vq, sd, vq_sd, ctx, dd = build_models(T, S, with_raft=False)
+    _, resp, use = R.respaced_schedule(ddpm_steps=S)
+    ref_model = R.RefModel(sd, dict(TINY_UNET, num_frames=T), dict(TINY_STRUCT, num_frames=T), resp, use, T)
+    lat, x = det_tensor("lat", (T, 4, h, w)).to(DEV), det_tensor("xT", (T, 4, h, w)).to(DEV)
+    ff = 1.5 * F.interpolate(det_tensor("ff", (T - 1, 2, 6, 5)), size=(h, w), mode="bicubic")[None].to(DEV)
+    fb = -ff + 0.2 * F.interpolate(det_tensor("fb", (T - 1, 2, 6, 5)), size=(h, w), mode="bicubic")[None].to(DEV)
+    occ = R.forward_backward_consistency_check(fb[:, 0], ff[:, 0])
+    masks = (occ[0][:, None, None], occ[1][:, None, None])
+    tw = R.gaussian_weights(64, 64, 1).to(DEV)
+    tile_weights = m._gaussian_weights(64, 64, 1)
+    g = torch.Generator().manual_seed(99)
+    worst = dict(frac=1.0, rel=0.0, frac_g=1.0, ratio=0.0)
+    for i in reversed(range(S)):
+        noise = torch.randn(T, 4, h, w, generator=g).to(DEV)
+        with torch.no_grad():
+            ref_plain, _ = ref_model.p_sample_canvas(x, ctx, lat, i, noise, None, None, -10.0, 64, 32, tw)
+            ref_guided, _ = ref_model.p_sample_canvas(x, ctx, lat, i, noise, (ff, fb), masks, -10.0, 64, 32, tw)
+            with torch.autocast("cuda", dtype=torch.float16):
+                ac_plain, _ = ref_model.p_sample_canvas(x, ctx, lat, i, noise, None, None, -10.0, 64, 32, tw)
+        ts = torch.full((1,), i, device=DEV, dtype=torch.long)
+        tr = torch.full((1,), m.ori_timesteps[i], device=DEV, dtype=torch.long)
+        kw = dict(t_replace=tr, tile_size=64, tile_overlap=32, batch_size=1, tile_weights=tile_weights, _step=i)
+        orig = m._step_noise
+        m._step_noise = lambda x_, n_, noise=noise: noise
+        try:
+            got_plain = m.p_sample_canvas(x, ctx, lat, ts, **kw)
+            got_guided = m.p_sample_canvas(x, ctx, lat, ts, guidance_scale=-10.0, flows=(ff, fb), masks=masks, **kw)
+        finally:
+            m._step_noise = orig
+        rng_ = ref_plain.abs().max().item()
+        e_got, e_ac = (got_plain - ref_plain).abs().max().item() / rng_, (ac_plain.float() - ref_plain).abs().max().item() / rng_
+        worst["frac"] = min(worst["frac"], close_frac(got_plain, ref_plain))
+        worst["rel"] = max(worst["rel"], e_got)
+        worst["ratio"] = max(worst["ratio"], e_got / max(e_ac, 1e-6))
+        worst["frac_g"] = min(worst["frac_g"], close_frac(got_guided, ref_guided))
+        x = ref_guided                                    # teacher forcing: the oracle's trajectory drives both
+    print("[teacher-forced 50 steps] worst over steps:", worst)
+    assert worst["rel"] < 3e-3, worst                     # max error / latent range, every step
+    assert worst["frac"] > 0.995, worst                   # fraction of elements inside rtol 3e-3 / atol 1e-4
+    assert worst["frac_g"] > 0.99, worst
+    assert worst["ratio"] < 2.0, worst                    # never more than 2x the error of the reference's own fp16 autocast
+
+
+@pytest.mark.parametrize("T,H,W", [(5, 512, 512), (2, 736, 960)])
+def test_full_size_vae_vs_oracle(T, H, W):
+    """SD-2.1 VAE shapes (ch 128, mult 1-2-4-4, mid attention C=512 single head: N=4096 at 512^2, N=11040 at a 736x960 tile):
+    AutoencoderKL.encode, VideoAutoencoderKLResi.encode / decode, AutoencoderKL.decode against the fp32 oracle (TF32 off)"""
+    import bench
+    from mgld_vsr_b200.autoencoder import AutoencoderKL, VideoAutoencoderKLResi
+    cfg = bench.load_cfg()
+    dd = dict(cfg.video_vae.params.ddconfig, num_frames=T)
+    ddk = dict(cfg.model.params.first_stage_config.params.ddconfig)
+    vq = VideoAutoencoderKLResi(ddconfig=dd, embed_dim=4)
+    sd = bench.fast_state_dict(vq.expected_shapes(), 2)
+    vq.load_state_dict(sd)
+    kl = AutoencoderKL(ddconfig=ddk, embed_dim=4)
+    sdk = bench.fast_state_dict(kl.expected_shapes(), 3)
+    kl.load_state_dict(sdk)
+    g = torch.Generator().manual_seed(5)
+    x = (F.interpolate(torch.rand(T, 3, H // 8, W // 8, generator=g), size=(H, W), mode="bicubic") * 2 - 1).clamp(-1, 1).to(DEV)
+    z = torch.randn(T, 4, H // 8, W // 8, generator=g).to(DEV)
+    sd_d, sdk_d = to_dev(sd), {"first_stage_model." + k: v.to(DEV) for k, v in sdk.items()}
+    with torch.no_grad():
+        post, fea = vq.encode(x)
+        mom, fea_ref = R.video_vae_encode(sd_d, dd, x)
+        e_enc = rel_err(post.parameters, mom)
+        e_fea = [rel_err(a, b) for a, b in zip(fea, fea_ref)]
+        dec = vq.decode(z, fea)
+        dec_ref = R.video_vae_decode(sd_d, dd, z, [f.float() for f in fea], 1.0)
+        e_dec = rel_err(dec, dec_ref)
+        e_kl = rel_err(kl.encode(x).parameters, R.autoencoder_kl_encode(sdk_d, ddk, x))
+        e_kld = rel_err(kl.decode(z), R.autoencoder_kl_decode(sdk_d, ddk, z))
+    print(f"[full-size VAE {T}x{H}x{W}] rel err: video enc moments {e_enc:.2e}, taps {e_fea}, video dec {e_dec:.2e}, "
+          f"KL enc {e_kl:.2e}, KL dec {e_kld:.2e}")
+    assert max([e_enc, e_dec, e_kl, e_kld] + e_fea) < 4e-3
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_sample_canvas_bitwise_repeatable(use_graph):
+    """same seed, same inputs -> the same bits: guidance accumulates in fixed point, split-K is two-pass, the norms reduce in
+    a fixed order (the fp64 atomics of the streaming GroupNorm sums round identically for all practical purposes)"""
+    T, S, h, w = 2, 4, 80, 72
+    m, vq, sd, vq_sd, ctx, dd = build_models(T, S, use_graph=use_graph, with_raft=False)
+    lat, x_T = det_tensor("lat", (T, 4, h, w)).to(DEV), det_tensor("xT", (T, 4, h, w)).to(DEV)
+    ff = 1.5 * F.interpolate(det_tensor("ff", (T - 1, 2, 6, 5)), size=(h, w), mode="bicubic")[None].to(DEV)
+    fb = -ff + 0.2 * F.interpolate(det_tensor("fb", (T - 1, 2, 6, 5)), size=(h, w), mode="bicubic")[None].to(DEV)
+    occ = R.forward_backward_consistency_check(fb[:, 0], ff[:, 0])
+    masks = (occ[0][:, None, None], occ[1][:, None, None])
+    outs = []
+    for _ in range(3):
+        torch.manual_seed(123)
+        outs.append(m.sample_canvas(cond=ctx, struct_cond=lat, guidance_scale=-10.0, flows=(ff, fb), masks=masks,
+                                    batch_size=T, timesteps=S, time_replace=S, x_T=x_T, tile_size=64, tile_overlap=32,
+                                    batch_size_sample=1))
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+def test_decode_first_stage_vs_oracle():
+    """LatentDiffusionVSRTextWT.decode_first_stage (ddpm.py:3786) = AutoencoderKL.decode(z / scale_factor)"""
+    T = 2
+    m, vq, sd, vq_sd, ctx, dd = build_models(T, 2, with_raft=False)
+    z = det_tensor("dfz", (T, 4, 16, 24)).to(DEV)
+    got = m.decode_first_stage(z)
+    with torch.no_grad():
+        ref = R.autoencoder_kl_decode(sd, dd, z / 0.18215)
+    assert got.shape == (T, 3, 128, 192) and rel_err(got, ref) < 4e-3

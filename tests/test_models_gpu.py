@@ -2,8 +2,10 @@
 plus the committed golden fixtures generated from the reference's own modules (tests/golden, tools/make_golden.py).
 
 Tolerance: the product runs fp16 storage / fp32 accumulation exactly like the reference under autocast; against the
-fp32 oracle that is ~1e-3 of the output range per network (north-star: rtol 3e-3 fp16); asserted at 1e-2 for whole
-networks and 2.5e-2 for the 3-step sampler whose last step amplifies differences ~460x."""
+TRUE-fp32 oracle (TF32 is switched off for every GPU test, tests/conftest.py) that is ~1-2e-3 of the output range per
+network (north-star: rtol 3e-3 fp16; measured 2.2e-3 at full size) — asserted at 4e-3 (NET_TOL) for whole networks.  The
+sampler with guidance is compared with robust statistics: its L1 sign() and ~460x last step turn an
+fp16-level difference into isolated O(0.05) pixel differences."""
 import os
 
 import pytest
@@ -16,6 +18,12 @@ from oracle import torch_ref as R
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 T = 2
+NET_TOL = 4e-3
+
+
+def robust_close(got, ref, mean_tol=2e-3, frac_tol=5e-3, thr=2e-2):
+    d = (got.float() - ref.float()).abs() / ref.abs().max()
+    return bool(d.mean() < mean_tol and (d > thr).float().mean() < frac_tol), (d.mean().item(), (d > thr).float().mean().item())
 
 
 def to_dev(sd):
@@ -33,17 +41,17 @@ def test_unet_and_struct_encoder_vs_oracle():
     feats = se(lat, t)
     ref_feats = R.struct_encoder_forward(to_dev(sd_s), TINY_STRUCT, lat, t, prefix="")
     for k in ref_feats:
-        assert rel_err(feats[k], ref_feats[k]) < 1e-2, k
+        assert rel_err(feats[k], ref_feats[k]) < NET_TOL, k
     sc = {"32": det_tensor("s32", (T, 64, 32, 32)).to(DEV), "16": det_tensor("s16", (T, 64, 16, 16)).to(DEV)}
     got = unet(x, t, ctx, sc)
     ref = R.unet_forward(to_dev(sd_u), TINY_UNET, x, t, ctx, sc, prefix="")
-    assert rel_err(got, ref) < 1e-2
+    assert rel_err(got, ref) < NET_TOL
     g = os.path.join(GOLDEN, "tiny_unet.pt")
     if os.path.exists(g):
         gold = torch.load(g)
-        assert rel_err(got.cpu(), gold["eps"]) < 1e-2
+        assert rel_err(got.cpu(), gold["eps"]) < NET_TOL
         for k in gold["struct"]:
-            assert rel_err(feats[k].cpu(), gold["struct"][k]) < 1e-2
+            assert rel_err(feats[k].cpu(), gold["struct"][k]) < NET_TOL
 
 
 def test_vae_vs_oracle():
@@ -54,20 +62,20 @@ def test_vae_vs_oracle():
     x, z = det_tensor("img", (T, 3, 64, 64)).clamp(-1, 1).to(DEV), det_tensor("z", (T, 4, 8, 8)).to(DEV)
     post, fea = vq.encode(x)
     mom, fea2 = R.video_vae_encode(to_dev(sd), TINY_DD, x)
-    assert rel_err(post.parameters, mom) < 1e-2
+    assert rel_err(post.parameters, mom) < NET_TOL
     for a, b in zip(fea, fea2):
-        assert rel_err(a, b) < 1e-2
+        assert rel_err(a, b) < NET_TOL
     dec = vq.decode(z, fea)
-    assert rel_err(dec, R.video_vae_decode(to_dev(sd), TINY_DD, z, fea2, 1.0)) < 1e-2
+    assert rel_err(dec, R.video_vae_decode(to_dev(sd), TINY_DD, z, fea2, 1.0)) < NET_TOL
     kl = AutoencoderKL(ddconfig=TINY_DD, embed_dim=4)
     sdk = det_state_dict(kl.expected_shapes())
     kl.load_state_dict(sdk)
     m2 = R.autoencoder_kl_encode({"first_stage_model." + k: v.to(DEV) for k, v in sdk.items()}, TINY_DD, x)
-    assert rel_err(kl.encode(x).parameters, m2) < 1e-2
+    assert rel_err(kl.encode(x).parameters, m2) < NET_TOL
     g = os.path.join(GOLDEN, "tiny_vae.pt")
     if os.path.exists(g):
         gold = torch.load(g)
-        assert rel_err(post.parameters.cpu(), gold["moments"]) < 1e-2 and rel_err(dec.cpu(), gold["dec"]) < 1e-2
+        assert rel_err(post.parameters.cpu(), gold["moments"]) < NET_TOL and rel_err(dec.cpu(), gold["dec"]) < NET_TOL
 
 
 def build_tiny_ldm(use_graph):
@@ -113,14 +121,14 @@ def test_sample_canvas_vs_oracle(use_graph):
     torch.manual_seed(123)
     got = m.sample_canvas(cond=ctx, struct_cond=lat, guidance_scale=-10.0, flows=(ff, fb), masks=(fo, bo), batch_size=T,
                           timesteps=S, time_replace=S, x_T=x_T, tile_size=32, tile_overlap=16, batch_size_sample=1)
-    assert rel_err(got, ref) < 2.5e-2
-    # same seed, same inputs -> same result up to fp32 atomic-add ordering in the guidance scatter, which the L1 sign()
-    # and the ~460x last step amplify
+    ok, stats = robust_close(got, ref)
+    assert ok, stats
+    # same seed, same inputs -> the same bits (the guidance scatter accumulates in 64-bit fixed point)
     torch.manual_seed(123)
     again = m.sample_canvas(cond=ctx, struct_cond=lat, guidance_scale=-10.0, flows=(ff, fb), masks=(fo, bo),
                             batch_size=T, timesteps=S, time_replace=S, x_T=x_T, tile_size=32, tile_overlap=16,
                             batch_size_sample=1)
-    assert rel_err(again, got) < 1e-2
+    assert torch.equal(again, got)
 
 
 def test_sample_untiled_runs_and_matches_canvas_single_tile():
@@ -146,11 +154,11 @@ def test_raft_vs_oracle_and_golden():
     a, b = det_tensor("raft_a", (2, 3, 128, 136)).sigmoid().to(DEV), det_tensor("raft_b", (2, 3, 128, 136)).sigmoid().to(DEV)
     got = m(a, b, iters=10)
     ref = R.raft_forward(to_dev(sd), a, b, iters=10)
-    assert rel_err(got, ref) < 1e-2
-    assert rel_err(got.cpu(), torch.load(os.path.join(GOLDEN, "raft.pt"))["flow"]) < 1e-2
+    assert rel_err(got, ref) < NET_TOL
+    assert rel_err(got.cpu(), torch.load(os.path.join(GOLDEN, "raft.pt"))["flow"]) < NET_TOL
     # odd sizes exercise the replicate padding and the non-16-byte-aligned correlation rows
     a, b = torch.rand(1, 3, 130, 150, device=DEV), torch.rand(1, 3, 130, 150, device=DEV)
-    assert rel_err(m(a, b, iters=3), R.raft_forward(to_dev(sd), a, b, iters=3)) < 1e-2
+    assert rel_err(m(a, b, iters=3), R.raft_forward(to_dev(sd), a, b, iters=3)) < NET_TOL
 
 
 def test_unet_two_clips_in_one_batch_vs_oracle():
@@ -166,7 +174,7 @@ def test_unet_two_clips_in_one_batch_vs_oracle():
     both = unet(x, t, ctx, se(lat, t))
     ref = R.unet_forward(to_dev(sd_u), TINY_UNET, x, t, ctx,
                          R.struct_encoder_forward(to_dev(sd_s), TINY_STRUCT, lat, t, prefix=""), prefix="")
-    assert rel_err(both, ref) < 1e-2
+    assert rel_err(both, ref) < NET_TOL
     for k in range(2):
         alone = unet(x[k * T:(k + 1) * T], t, ctx, se(lat[k * T:(k + 1) * T], t))
         assert rel_err(both[k * T:(k + 1) * T], alone) < 5e-3     # tile plans differ with the row count: fp16 rounding only
@@ -207,7 +215,8 @@ def test_sample_canvas_num_clips_equals_clip_by_clip(use_graph):
     for k, (lat, x_T, (ff, fb, fo, bo)) in enumerate(clips):
         torch.manual_seed(7)
         one = m.sample_canvas(struct_cond=lat, x_T=x_T, flows=(ff, fb), masks=(fo, bo), **kw)
-        assert rel_err(got_g[k * T:(k + 1) * T], one) < 2.5e-2
+        ok, stats = robust_close(got_g[k * T:(k + 1) * T], one)
+        assert ok, stats
 
 
 @pytest.mark.parametrize("num_clips", [1, 2])
@@ -251,15 +260,14 @@ def test_full_size_tile_step_vs_oracle():
     x, lat = det_tensor("fx", (n, 4, 64, 64)).to(DEV), det_tensor("flat", (n, 4, 64, 64)).to(DEV)
     ctx, t = det_tensor("fctx", (1, 77, 1024)).to(DEV), torch.tensor([481], device=DEV)
     got = unet(x, t, ctx, se(lat, t))
-    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
-    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
-    try:
-        with torch.no_grad():
-            ucfg, scfg = dict(mp.unet_config.params), dict(mp.structcond_stage_config.params)
-            feats = R.struct_encoder_forward(to_dev(sd_s), scfg, lat, t, prefix="")
-            ref = R.unet_forward(to_dev(sd_u), ucfg, x, t, ctx, feats, prefix="")
-    finally:
-        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
-    e = rel_err(got, ref)
-    print(f"full-size tile-step rel err vs fp32 oracle: {e:.3e}")
-    assert torch.isfinite(got).all() and e < 1e-2, e      # measured 2.2e-3 (north-star tolerance rtol 3e-3)
+    assert not torch.backends.cudnn.allow_tf32 and not torch.backends.cuda.matmul.allow_tf32   # conftest autouse fixture
+    with torch.no_grad():
+        ucfg, scfg = dict(mp.unet_config.params), dict(mp.structcond_stage_config.params)
+        feats = R.struct_encoder_forward(to_dev(sd_s), scfg, lat, t, prefix="")
+        ref = R.unet_forward(to_dev(sd_u), ucfg, x, t, ctx, feats, prefix="")
+        with torch.autocast("cuda", dtype=torch.float16):             # the reference's deployment numerics, as a yardstick
+            ac = R.unet_forward(to_dev(sd_u), ucfg, x, t, ctx, R.struct_encoder_forward(to_dev(sd_s), scfg, lat, t, prefix=""),
+                                prefix="")
+    e, e_ac = rel_err(got, ref), rel_err(ac.float(), ref)
+    print(f"full-size tile-step rel err vs fp32 oracle: {e:.3e} (oracle under fp16 autocast: {e_ac:.3e})")
+    assert torch.isfinite(got).all() and e < 3e-3, e      # north-star tolerance rtol 3e-3; measured 2.2e-3

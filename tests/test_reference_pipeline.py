@@ -93,7 +93,17 @@ CASES = {
 }
 
 
+_REF_RUNS = {}
+
+
 def run_reference_case(ref_models, name, S=2):
+    """the reference script's own segment loop on case `name` (run once per session, reused by the tests below)"""
+    if (name, S) not in _REF_RUNS:
+        _REF_RUNS[(name, S)] = _run_reference_case(ref_models, name, S)
+    return _REF_RUNS[(name, S)]
+
+
+def _run_reference_case(ref_models, name, S):
     import ref_harness as H
     model, vq, sd, vq_sd, sa, s1, ctx = ref_models[S]
     Hh, Ww, ts, st, cf, us = CASES[name]
