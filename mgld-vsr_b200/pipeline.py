@@ -205,33 +205,53 @@ class VSRPipeline:
         """one VAE tile of one segment: script :428-473"""
         return self._sr_units([(im_lq_pch, flow_f, flow_b, fwd_occ, bwd_occ)], context)[0]
 
-    # ---- script :375-535 for one segment, split into "cut into units" and "assemble" so that units of several segments
-    # can be batched --------------------------------------------------------------------------------------------------
-    def _segment_units(self, init_image, flows_override=None, use_guidance=True):
+    # ---- script :375-535 for one segment, split into "geometry" (pad, VAE-tile boxes: no GPU work), "cut into units"
+    # (flow estimation + tile crops, only for the units this rank owns) and "assemble", so that units of several segments
+    # can be batched and sharded over ranks --------------------------------------------------------------------------
+    def _segment_geometry(self, init_image):
         im = init_image.clamp(-1.0, 1.0)
         ori_h, ori_w = im.shape[2:]
         flag_pad = not (ori_h % 32 == 0 and ori_w % 32 == 0)
         if flag_pad:                                                              # quirk D13: both dims grow
             im = F.pad(im, pad=(0, ((ori_w // 32) + 1) * 32 - ori_w, 0, ((ori_h // 32) + 1) * 32 - ori_h), mode="reflect")
+        tiled = im.shape[2] > self.tile or im.shape[3] > self.tile
+        sp = ImageSpliterTh(im, self.tile, self.stride, sf=1) if tiled else None
+        return dict(im=im, ori=(ori_h, ori_w), flag_pad=flag_pad, sp=sp, infos=[], n_units=len(sp) if tiled else 1)
+
+    def _segment_units(self, init_image, flows_override=None, use_guidance=True, only=None, meta=None):
+        """-> (meta, units).  `only`: local unit indices wanted (default all); RAFT runs only if any unit is wanted."""
+        meta = self._segment_geometry(init_image) if meta is None else meta
+        im, sp = meta["im"], meta["sp"]
+        want = list(range(meta["n_units"])) if only is None else sorted(only)
+        if not want:
+            return meta, []
         if use_guidance and im.shape[0] > 1:
             flows, (fwd_occs, bwd_occs) = self.estimate_flows(im, flows_override)
         else:
             flows, fwd_occs, bwd_occs = [None, None], None, None
-        sp, units, infos = None, [], []
-        if im.shape[2] > self.tile or im.shape[3] > self.tile:
-            sp = ImageSpliterTh(im, self.tile, self.stride, sf=1)
+        units = []
+        if sp is not None:
             aux = [ImageSpliterTh(t, self.tile // 8, self.stride // 8, sf=1) if t is not None else None
                    for t in (flows[0], flows[1], fwd_occs, bwd_occs)]               # quirk D10: 750 // 8 = 93
-            for pch, index_infos in sp:
-                units.append((pch, *[next(a)[0] if a is not None else None for a in aux]))
-                infos.append(index_infos)
+            meta["infos"] = []
+            for k, (pch, index_infos) in enumerate(sp):
+                cuts = [next(a)[0] if a is not None else None for a in aux]
+                meta["infos"].append(index_infos)
+                if k in want:
+                    units.append((pch, *cuts))
+            sp.num_pchs = 0
         else:
             units.append((im, flows[0], flows[1], fwd_occs, bwd_occs))            # D2 resolved
-        return dict(im=im, ori=(ori_h, ori_w), flag_pad=flag_pad, sp=sp, infos=infos), units
+        return meta, units
 
     def _segment_assemble(self, meta, tiles):
         im, sp = meta["im"], meta["sp"]
         if sp is not None:
+            if not meta["infos"]:                                                 # geometry only (another rank cut the units)
+                meta["infos"] = [info for _, info in sp]
+                sp.num_pchs = 0
+            sp.im_res.zero_()
+            sp.pixel_count.zero_()
             for x, index_infos in zip(tiles, meta["infos"]):
                 sp.update(x, index_infos)
             x = sp.gather()
@@ -253,22 +273,76 @@ class VSRPipeline:
         return self._segment_assemble(meta, self._sr_units(units, context))
 
     @torch.no_grad()
-    def __call__(self, frames, context=None, flows_override=None, use_guidance=True):
-        """frames (N,3,h,w) in [-1,1] on the model's device -> (N,3,H,W) in [0,1]"""
+    def __call__(self, frames, context=None, flows_override=None, use_guidance=True, world_size=1, rank=0, group=None):
+        """frames (N,3,h,w) in [-1,1] on the model's device -> (N,3,H,W) in [0,1].
+
+        world_size > 1 (one process per GPU, every rank holds the LR clip and calls this): ONE clip is sharded over the
+        ranks at the granularity of its independent units (segment x VAE tile; SURVEY.md §8e axes 1 and 2) in contiguous
+        blocks — a rank then estimates flow only for the few segments its units belong to — and the finished tiles are
+        exchanged with a single all-gather per tile shape; every rank assembles the whole clip."""
         if context is None:
             context = self.model.cond_stage_model([""])
         segs, n = self.segments(frames)
-        metas, units, owner = [], [], []
+        metas = [self._segment_geometry(seg) for seg in segs]
+        owner = [si for si, m in enumerate(metas) for _ in range(m["n_units"])]
+        first = [0]
+        for m in metas:
+            first.append(first[-1] + m["n_units"])
+        lo, hi = shard_units(len(owner), world_size, rank)
+        units = []
         for si, seg in enumerate(segs):
+            only = [u - first[si] for u in range(lo, hi) if owner[u] == si]
             fo = None if flows_override is None else flows_override[si]
-            meta, u = self._segment_units(seg, fo, use_guidance)
-            metas.append(meta)
-            owner += [si] * len(u)
-            units += u
+            units += self._segment_units(seg, fo, use_guidance, only=only, meta=metas[si])[1]
         tiles = self._sr_units(units, context)
-        outs = [self._segment_assemble(meta, [t for t, o in zip(tiles, owner) if o == si])
-                for si, meta in enumerate(metas)]
+        if world_size > 1:
+            tiles = gather_units(tiles, [tuple(u_shape) for u_shape in self._unit_out_shapes(metas)], world_size, rank,
+                                 frames.device, group)
+        outs = [self._segment_assemble(meta, tiles[first[si]:first[si + 1]]) for si, meta in enumerate(metas)]
         return torch.cat(outs, 0)[:n]
+
+    def _unit_out_shapes(self, metas):
+        """decoded-tile shape (T,3,th,tw) of every unit in global order (geometry only: known on every rank)"""
+        shapes = []
+        for m in metas:
+            im, sp = m["im"], m["sp"]
+            if sp is None:
+                shapes.append(tuple(im.shape))
+            else:
+                th, tw = min(self.tile, im.shape[2]), min(self.tile, im.shape[3])
+                shapes += [(im.shape[0], im.shape[1], th, tw)] * m["n_units"]
+        return shapes
+
+
+def shard_units(num_units, world_size, rank):
+    """contiguous block [lo, hi) of the global unit list owned by `rank` (block sizes differ by at most one)"""
+    return (num_units * rank) // world_size, (num_units * (rank + 1)) // world_size
+
+
+def gather_units(local_tiles, shapes, world_size, rank, device, group=None):
+    """All-gather the decoded tiles of one clip.  `shapes`: output shape of every unit in global order; this rank passes the
+    tiles of its `shard_units` block.  One collective per distinct tile shape (one, for the shipped configurations);
+    returns the list of all tiles in global order on every rank (fp32: the N-GPU clip equals the 1-GPU clip)."""
+    import torch.distributed as dist
+    n = len(shapes)
+    lo, hi = shard_units(n, world_size, rank)
+    assert len(local_tiles) == hi - lo
+    out = [None] * n
+    for shp in sorted(set(shapes)):
+        idx = [u for u in range(n) if shapes[u] == shp]
+        per_rank = [[u for u in idx if shard_units(n, world_size, r)[0] <= u < shard_units(n, world_size, r)[1]]
+                    for r in range(world_size)]
+        slots = max(len(p) for p in per_rank)
+        buf = torch.zeros(slots, *shp, dtype=torch.float32, device=device)
+        for k, u in enumerate(per_rank[rank]):
+            buf[k] = local_tiles[u - lo]
+        allbuf = torch.empty(world_size * slots, *shp, dtype=torch.float32, device=device)
+        dist.all_gather_into_tensor(allbuf, buf, group=group)
+        allbuf = allbuf.view(world_size, slots, *shp)
+        for r in range(world_size):
+            for k, u in enumerate(per_rank[r]):
+                out[u] = allbuf[r, k]
+    return out
 
 
 def shard_segments(num_segments, world_size, rank):

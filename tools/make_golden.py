@@ -101,7 +101,9 @@ def make_pipeline_golden():
     resolution crop, fp16) for the GPU box, where /root/reference does not exist."""
     import ref_harness as H
     from test_reference_pipeline import CASES, lr_segment
-    T, S = 2, 4
+    # 2 steps: a free-running sampler amplifies an fp16-level eps difference ~3x at its first (t=999) step and then through
+    # every later network evaluation, so longer free runs are compared statistically (tests/test_e2e_gpu.py), not per pixel
+    T, S = 2, 2
     ctx = det_tensor("ctx", (1, 77, 128))
     model, vq, sd, vq_sd, sa, s1 = H.build_reference_models(T, ctx, S)
     caps, orig = [], model.sample_canvas
