@@ -146,6 +146,11 @@ int mgld_fb_consistency_f32(const float* fwd_flow, const float* bwd_flow, float*
 int mgld_motion_guidance_f32(const float* latents, const float* flow_fwd_prop, const float* flow_bwd_prop,
                              const float* fwd_occ, const float* bwd_occ, void* grad_ws, float* out, float* grad_out,
                              float* loss, float step, int t, int c, int h, int w, void* stream);
+/* Graph-replayable form of mgld_motion_guidance_f32: the step scalar is read on the device as step_table[*step_idx], so
+ * one captured launch sequence serves every DDPM step.                                                                */
+int mgld_motion_guidance_dev_f32(const float* latents, const float* flow_fwd_prop, const float* flow_bwd_prop,
+                                 const float* fwd_occ, const float* bwd_occ, void* grad_ws, float* out,
+                                 const float* step_table, const int* step_idx, int t, int c, int h, int w, void* stream);
 /* basicsr/archs/arch_util.py:235 resize_flow (bilinear, align_corners=False, values scaled by the size ratio)        */
 int mgld_resize_flow_f32(const float* flow, float* out, int n, int h, int w, int oh, int ow, void* stream);
 /* ddpm.py:4275-4316 + 4404-4417: Gaussian-weighted stitch of eps tiles, x0, posterior mean, noise add.
@@ -155,12 +160,21 @@ int mgld_canvas_posterior_f32(const float* x, const float* const* eps_tiles_dev,
                               const float* noise, float* out, float* eps_out, int n_tiles, const int* ofs_x,
                               const int* ofs_y, int tc, int h, int w, int tile_size, float c_recip, float c_recipm1,
                               float c1, float c2, float sigma, void* stream);
+/* Graph-replayable form: the five per-step scalars are read on the device from coef_table[5 * *step_idx + {0..4}]
+ * (c_recip, c_recipm1, c1, c2, sigma), the noise of this step from noise_all + *step_idx * noise_step_stride, laid out
+ * (noise_tc, h, w) and shared by the tc / noise_tc clips batched in the canvas (they are re-seeded identically).        */
+int mgld_canvas_posterior_dev_f32(const float* x, const float* const* eps_tiles_dev, const double* tile_w,
+                                  const float* noise_all, long long noise_step_stride, int noise_tc, float* out,
+                                  int n_tiles, const int* ofs_x, const int* ofs_y, int tc, int h, int w, int tile_size,
+                                  const float* coef_table, const int* step_idx, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Normalisation (fp16 NHWC activations, fp32 math)
  * ------------------------------------------------------------------------------------------------------------------ */
-/* GroupNorm statistics over the virtual concat [x1 | x2] (x2 may be NULL): sums[t][g] += (sum, sum of squares) in
- * double; the caller zeroes `sums` ([T, groups, 2] doubles).  GroupNorm32 util.py:199-216 / Normalize model.py:80.     */
+/* GroupNorm statistics over the virtual concat [x1 | x2] (x2 may be NULL): sums[t][g] += (sum, sum of squares).  `sums` is
+ * an opaque array of [T, groups, 2] ACCUMULATORS OF 16 BYTES each (integer part + 2^-40 fixed-point fraction, summed with
+ * integer atomics: the statistics are bitwise repeatable), i.e. T*groups*4 doubles' worth of memory, zeroed by the caller.
+ * GroupNorm32 util.py:199-216 / Normalize model.py:80.                                                                */
 int mgld_gn_stats_f16(const void* x1, int C1, int ld1, const void* x2, int C2, int ld2, int T, int HW, int groups,
                       double* sums, void* stream);
 /* (sum, sumsq) -> fp32 (mean, rstd) pairs, for the SPADE epilogue of mgld_conv_gemm                                  */

@@ -66,6 +66,23 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // launch attribute off (the device instructions are then no-ops).
 bool pdl_enabled();
 #ifdef __CUDACC__
+// Order-independent (bitwise repeatable) accumulation of fp32 partial sums across thread blocks: a value is split exactly
+// into its integer part and a 40-bit fixed-point fraction, each accumulated with 64-bit INTEGER atomics (associative and
+// commutative, unlike floating-point atomics).  One accumulator = two 8-byte words {integer part, fraction * 2^40}; zero
+// bytes = zero.  Range: |sum of integer parts| < 2^63; resolution 2^-40.  Used for the GroupNorm / InstanceNorm sums.
+__device__ __forceinline__ void fixsum_add(double* acc, float p) {
+  const float fl = floorf(p);
+  const long long hi = __float2ll_rd(p);
+  const long long lo = __double2ll_rd((double)(p - fl) * 1099511627776.0);
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(acc);
+  atomicAdd(a, (unsigned long long)hi);
+  atomicAdd(a + 1, (unsigned long long)lo);
+}
+__device__ __forceinline__ double fixsum_load(const double* acc) {
+  const long long* a = reinterpret_cast<const long long*>(acc);
+  return (double)a[0] + (double)a[1] * (1.0 / 1099511627776.0);
+}
+
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 template <typename... P, typename... A>

@@ -241,8 +241,10 @@ __global__ void motion_guidance_grad_kernel(const float* __restrict__ z, const f
 // loss_f32 (optional) the loss; both alias the head of the workspace, which is why thread 0 converts the loss last.
 __global__ void axpy_update_kernel(const float* __restrict__ z, const long long* __restrict__ grad,
                                    float* __restrict__ out, float* __restrict__ grad_f32, float step, int n,
-                                   const long long* __restrict__ loss_fix, float* __restrict__ loss_f32) {
+                                   const long long* __restrict__ loss_fix, float* __restrict__ loss_f32,
+                                   const float* __restrict__ step_table, const int* __restrict__ step_idx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (step_table) step = step_table[*step_idx];    // graph-replayable form: the per-step scalar lives in device memory
   if (i < n) {
     const float g = (float)((double)grad[i] * (1.0 / kFixScale));
     out[i] = __fadd_rn(z[i], -__fmul_rn(step, g));
@@ -286,11 +288,20 @@ __global__ void canvas_posterior_kernel(const float* __restrict__ x, const float
                                         const double* __restrict__ tile_w, const float* __restrict__ noise,
                                         float* __restrict__ out, float* __restrict__ eps_out, TileList tl, int TC,
                                         int H, int W, int ts, float c_recip, float c_recipm1, float c1, float c2,
-                                        float sigma) {
+                                        float sigma, const float* __restrict__ coef_table,
+                                        const int* __restrict__ step_idx, long long noise_step_stride, int noise_rep) {
   const int hw = H * W;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const int tc = blockIdx.y;
   if (p >= hw) return;
+  int tc_noise = tc;
+  if (coef_table) {   // graph-replayable form: per-step scalars and this step's noise slice are picked on the device
+    const int st = *step_idx;
+    const float* c = coef_table + 5 * st;
+    c_recip = c[0]; c_recipm1 = c[1]; c1 = c[2]; c2 = c[3]; sigma = c[4];
+    noise += static_cast<long long>(st) * noise_step_stride;
+    tc_noise = tc % noise_rep;     // clips batched in one canvas share one draw (the script re-seeds per clip, :428)
+  }
   const int px = p % W, py = p / W;
   float acc = 0.f, cnt = 0.f;
   for (int i = 0; i < tl.n; ++i) {
@@ -309,7 +320,7 @@ __global__ void canvas_posterior_kernel(const float* __restrict__ x, const float
   const float x0 = __fadd_rn(__fmul_rn(c_recip, xv), -__fmul_rn(c_recipm1, eps));
   const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xv));
   if (eps_out) eps_out[idx] = eps;
-  out[idx] = noise ? __fadd_rn(mean, __fmul_rn(sigma, noise[idx])) : mean;
+  out[idx] = noise ? __fadd_rn(mean, __fmul_rn(sigma, noise[static_cast<long long>(tc_noise) * hw + p])) : mean;
 }
 
 }  // namespace mgld
@@ -367,7 +378,28 @@ extern "C" int mgld_motion_guidance_f32(const float* latents, const float* flow_
                                                                               t, c, h, w);
     MGLD_LAUNCH_CHECK("motion_guidance_grad_kernel");
   }
-  axpy_update_kernel<<<(n + 255) / 256, 256, 0, s>>>(latents, acc, out, grad_out, step, n, acc + n, loss);
+  axpy_update_kernel<<<(n + 255) / 256, 256, 0, s>>>(latents, acc, out, grad_out, step, n, acc + n, loss, nullptr, nullptr);
+  MGLD_LAUNCH_CHECK("axpy_update_kernel");
+  return MGLD_OK;
+}
+
+extern "C" int mgld_motion_guidance_dev_f32(const float* latents, const float* flow_fwd_prop, const float* flow_bwd_prop,
+                                            const float* fwd_occ, const float* bwd_occ, void* grad_ws, float* out,
+                                            const float* step_table, const int* step_idx, int t, int c, int h, int w,
+                                            void* stream) {
+  MGLD_CHECK_ARG(latents && grad_ws && out && step_table && step_idx && t >= 2 && c > 0 && h > 0 && w > 0,
+                 "motion_guidance_dev: bad arguments");
+  MGLD_CHECK_ARG(flow_fwd_prop && flow_bwd_prop && fwd_occ && bwd_occ, "motion_guidance_dev: null flows");
+  MGLD_CHECK_ARG((reinterpret_cast<uintptr_t>(grad_ws) & 7) == 0, "motion_guidance_dev: workspace must be 8-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n = t * c * h * w;
+  long long* acc = static_cast<long long*>(grad_ws);
+  MGLD_CUDA(cudaMemsetAsync(acc, 0, sizeof(long long) * ((size_t)n + 1), s));
+  motion_guidance_grad_kernel<<<pix_grid(h * w, 2 * (t - 1)), 256, 0, s>>>(latents, flow_fwd_prop, flow_bwd_prop, fwd_occ,
+                                                                            bwd_occ, acc, nullptr, t, c, h, w);
+  MGLD_LAUNCH_CHECK("motion_guidance_grad_kernel");
+  axpy_update_kernel<<<(n + 255) / 256, 256, 0, s>>>(latents, acc, out, nullptr, 0.f, n, acc + n, nullptr, step_table,
+                                                     step_idx);
   MGLD_LAUNCH_CHECK("axpy_update_kernel");
   return MGLD_OK;
 }
@@ -390,7 +422,25 @@ extern "C" int mgld_canvas_posterior_f32(const float* x, const float* const* eps
   tl.n = n_tiles;
   for (int i = 0; i < n_tiles; ++i) { tl.ox[i] = ofs_x[i]; tl.oy[i] = ofs_y[i]; }
   canvas_posterior_kernel<<<pix_grid(h * w, tc), 256, 0, (cudaStream_t)stream>>>(
-      x, eps_tiles_dev, tile_w, noise, out, eps_out, tl, tc, h, w, tile_size, c_recip, c_recipm1, c1, c2, sigma);
+      x, eps_tiles_dev, tile_w, noise, out, eps_out, tl, tc, h, w, tile_size, c_recip, c_recipm1, c1, c2, sigma, nullptr,
+      nullptr, 0, tc);
+  MGLD_LAUNCH_CHECK("canvas_posterior_kernel");
+  return MGLD_OK;
+}
+
+extern "C" int mgld_canvas_posterior_dev_f32(const float* x, const float* const* eps_tiles_dev, const double* tile_w,
+                                             const float* noise_all, long long noise_step_stride, int noise_tc,
+                                             float* out, int n_tiles, const int* ofs_x, const int* ofs_y, int tc, int h,
+                                             int w, int tile_size, const float* coef_table, const int* step_idx,
+                                             void* stream) {
+  MGLD_CHECK_ARG(x && eps_tiles_dev && tile_w && out && noise_all && coef_table && step_idx && n_tiles > 0 && n_tiles <= 64 &&
+                     noise_tc > 0 && tc % noise_tc == 0, "canvas_posterior_dev: bad arguments");
+  TileList tl;
+  tl.n = n_tiles;
+  for (int i = 0; i < n_tiles; ++i) { tl.ox[i] = ofs_x[i]; tl.oy[i] = ofs_y[i]; }
+  canvas_posterior_kernel<<<pix_grid(h * w, tc), 256, 0, (cudaStream_t)stream>>>(
+      x, eps_tiles_dev, tile_w, noise_all, out, nullptr, tl, tc, h, w, tile_size, 0.f, 0.f, 0.f, 0.f, 0.f, coef_table,
+      step_idx, noise_step_stride, noise_tc);
   MGLD_LAUNCH_CHECK("canvas_posterior_kernel");
   return MGLD_OK;
 }

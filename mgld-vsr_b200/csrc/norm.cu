@@ -41,19 +41,20 @@ __device__ __forceinline__ uint4 load_cat8(const __half* x1, int C1, int ld1, co
 constexpr int kGnRowsPerBlock = 64;
 constexpr int kGnApplyItems = 1024;  // 8-channel vectors per block in gn_apply
 
-// sums[t][g] += (sum, sumsq) over rows [r0, r0+64) of frame t.  Double accumulation across blocks.
+// sums[t][g] += (sum, sumsq) over rows [r0, r0+64) of frame t.  Bitwise repeatable: fixed-order reduction inside the block
+// (per-thread channel partials -> shared table -> one thread per (group, moment) sums them in a fixed order) and
+// order-independent fixed-point accumulation across blocks (fixsum_add, common.h).  `sums`: [T, G, 2] accumulators of two
+// 8-byte words each.
 __global__ void gn_stats_kernel(const __half* __restrict__ x1, int C1, int ld1, const __half* __restrict__ x2, int C2,
                                 int ld2, int HW, int G, double* __restrict__ sums) {
   pdl_launch_dependents();
   pdl_wait();
 
-  extern __shared__ float sh[];  // [2*G]
+  extern __shared__ float sh[];  // [rpi * vpr][16]: per-thread (sum[8] | sumsq[8]) of its channel vector
   const int C = C1 + C2, vpr = C >> 3, cpg = C / G;
   const int t = blockIdx.y;
   const int r0 = blockIdx.x * kGnRowsPerBlock;
   const int rows = min(kGnRowsPerBlock, HW - r0);
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
   // thread -> fixed channel vector, strided rows: per-channel fp32 partials stay in registers
   const int rpi = blockDim.x / vpr;  // rows handled per iteration (>= 1 because blockDim >= vpr)
   const int v = threadIdx.x % vpr, rr = threadIdx.x / vpr;
@@ -81,19 +82,22 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, int C1, int ld1, 
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
     }
-    // fold channels of the same group before touching shared memory
-    int g_prev = (v * 8) / cpg;
-    float as = 0.f, aq = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int g = (v * 8 + i) / cpg;
-      if (g != g_prev) { atomicAdd(&sh[2 * g_prev], as); atomicAdd(&sh[2 * g_prev + 1], aq); as = 0.f; aq = 0.f; g_prev = g; }
-      as += s[i]; aq += q[i];
-    }
-    atomicAdd(&sh[2 * g_prev], as); atomicAdd(&sh[2 * g_prev + 1], aq);
+    float4* dst = reinterpret_cast<float4*>(sh + (rr * vpr + v) * 16);
+    dst[0] = make_float4(s[0], s[1], s[2], s[3]);
+    dst[1] = make_float4(s[4], s[5], s[6], s[7]);
+    dst[2] = make_float4(q[0], q[1], q[2], q[3]);
+    dst[3] = make_float4(q[4], q[5], q[6], q[7]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&sums[static_cast<long long>(t) * 2 * G + i], (double)sh[i]);
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) {   // i = 2 * group + moment
+    const int g = i >> 1, mo = (i & 1) * 8;
+    float acc = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      const float* col = sh + (c >> 3) * 16 + mo + (c & 7);
+      for (int k = 0; k < rpi; ++k) acc += col[k * vpr * 16];
+    }
+    fixsum_add(sums + (static_cast<long long>(t) * 2 * G + i) * 2, acc);
+  }
 }
 
 // (sum, sumsq) -> (mean, rstd) fp32
@@ -104,8 +108,8 @@ __global__ void gn_finalize_kernel(const double* __restrict__ sums, float* __res
 
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const double mean = sums[2 * i] / count;
-  double var = sums[2 * i + 1] / count - mean * mean;
+  const double mean = fixsum_load(sums + 4 * i) / count;
+  double var = fixsum_load(sums + 4 * i + 2) / count - mean * mean;
   if (var < 0.0) var = 0.0;
   stats[2 * i] = (float)mean;
   stats[2 * i + 1] = (float)(1.0 / sqrt(var + eps));
@@ -146,8 +150,8 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int C1, int ld1, 
   if (base == base0) {   // (mean, rstd) of the frame's groups, while the first loads are in flight
     const double count = (double)HW * cpg;
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
-      const double mean = sums[(static_cast<long long>(t) * G + g) * 2] / count;
-      double var = sums[(static_cast<long long>(t) * G + g) * 2 + 1] / count - mean * mean;
+      const double mean = fixsum_load(sums + (static_cast<long long>(t) * G + g) * 4) / count;
+      double var = fixsum_load(sums + (static_cast<long long>(t) * G + g) * 4 + 2) / count - mean * mean;
       if (var < 0.0) var = 0.0;
       sh[2 * g] = (float)mean;
       sh[2 * g + 1] = (float)(1.0 / sqrt(var + eps));
@@ -430,11 +434,11 @@ extern "C" int mgld_gn_stats_f16(const void* x1, int C1, int ld1, const void* x2
                                  int groups, double* sums, void* stream) {
   const int C = C1 + C2;
   MGLD_CHECK_ARG(x1 && sums && T > 0 && HW > 0 && groups > 0, "gn_stats: bad arguments");
-  MGLD_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0 && C % groups == 0 && C / 8 <= 1024, "gn_stats: C1=%d C2=%d G=%d", C1, C2,
+  MGLD_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0 && C % groups == 0 && C / 8 <= 704, "gn_stats: C1=%d C2=%d G=%d", C1, C2,
                  groups);
   MGLD_CHECK_ARG((C2 > 0) == (x2 != nullptr), "gn_stats: x2/C2 mismatch");
   dim3 grid(ceil_div(HW, kGnRowsPerBlock), T);
-  MGLD_CUDA(launch_pdl(gn_stats_kernel, grid, dim3(gn_threads(C)), 2 * groups * sizeof(float), (cudaStream_t)stream,
+  MGLD_CUDA(launch_pdl(gn_stats_kernel, grid, dim3(gn_threads(C)), gn_threads(C) * 16 * sizeof(float), (cudaStream_t)stream,
                        (const __half*)x1, C1, ld1 > 0 ? ld1 : C1, (const __half*)x2, C2, ld2 > 0 ? ld2 : C2, HW, groups, sums));
   MGLD_LAUNCH_CHECK("gn_stats_kernel");
   return MGLD_OK;
@@ -518,8 +522,8 @@ extern "C" int mgld_group_norm_f16(const void* x1, int C1, int ld1, const void* 
   memset(&p, 0, sizeof(p));
   int items = 0, csplit = 0;
   if (!gn_fused_plan(C, T, HW, groups, &p, &items, &csplit)) {
-    // multi-pass path: the caller's zeroed scratch ([T, groups, 2] doubles) carries the sums between the kernels
-    MGLD_CHECK_ARG(scratch, "group_norm: this shape needs the [T, groups, 2] fp64 scratch (zeroed)");
+    // multi-pass path: the caller's zeroed scratch ([T, groups, 2] accumulators of 16 bytes) carries the sums between the kernels
+    MGLD_CHECK_ARG(scratch, "group_norm: this shape needs the [T, groups, 2] x 16-byte scratch (zeroed)");
     int rc = mgld_gn_stats_f16(x1, C1, ld1, x2, C2, ld2, T, HW, groups, scratch, stream);
     if (rc) return rc;
     if (stats_out) { rc = mgld_gn_finalize(scratch, stats_out, T, groups, HW, C, eps, stream); if (rc) return rc; }

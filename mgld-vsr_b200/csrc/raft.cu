@@ -53,14 +53,14 @@ __global__ void subsample2_kernel(const uint4* __restrict__ in, uint4* __restric
   }
 }
 
-// instance norm (no affine) from per-(n, channel) fp64 sums [N, C, 2] (mgld_gn_stats_f16 with groups = C) + optional ReLU
+// instance norm (no affine) from per-(n, channel) fixed-point sums [N, C, 2] x 16 bytes (mgld_gn_stats_f16 with groups = C) + optional ReLU
 __global__ void inorm_apply_kernel(const __half* __restrict__ x, const double* __restrict__ sums, __half* __restrict__ out,
                                    int HW, int C, double eps, int relu) {
   extern __shared__ float sh[];  // [2*C] mean, rstd
   const int n = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const double mean = sums[(static_cast<long long>(n) * C + c) * 2] / HW;
-    double var = sums[(static_cast<long long>(n) * C + c) * 2 + 1] / HW - mean * mean;
+    const double mean = fixsum_load(sums + (static_cast<long long>(n) * C + c) * 4) / HW;
+    double var = fixsum_load(sums + (static_cast<long long>(n) * C + c) * 4 + 2) / HW - mean * mean;
     if (var < 0.0) var = 0.0;
     sh[2 * c] = (float)mean;
     sh[2 * c + 1] = (float)(1.0 / sqrt(var + eps));

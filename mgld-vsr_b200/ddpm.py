@@ -194,6 +194,117 @@ class _EpsRunner:
         return P["outs"][cur].clone()
 
 
+class _StepRunner:
+    """ONE CUDA-graph replay per DDPM step: every tile evaluation (struct-cond encoder + UNet), the Gaussian stitch + x0 +
+    posterior + noise add, and the motion guidance of every clip, with the latent canvas updated in place.  What changes
+    from step to step lives in device memory and is picked by a device step index: the timestep fed to the nets, the five
+    posterior scalars, the guidance step, and the slice of the pre-drawn noise (drawn up front in step order from the same
+    generator, so the stream equals the reference's per-step `noise_like` draws, ddpm.py:4404).  The host does one 4-byte
+    fill + one graph launch per step: no per-step allocation, pointer-table upload or eager launch keeps the GPU waiting."""
+
+    def __init__(self, model):
+        self.m = model
+        self.cache = {}
+
+    def clear(self):
+        self.cache.clear()
+
+    def _build(self, key, x, struct_cond, context, flows, masks, tile_size, tile_overlap, num_clips, S):
+        m, ops = self.m, self.m.ops
+        dev = x.device
+        B, C, h, w = x.shape
+        T1 = B // num_clips
+        offsets = m._tile_offsets(h, w, tile_size, tile_overlap)
+        st = dict(xb=x.clone(), scb=struct_cond.clone(), lat=torch.empty_like(x),
+                  noise=torch.empty(S, T1, C, h, w, device=dev), coef=torch.zeros(S, 5, device=dev),
+                  gstep=torch.zeros(S, device=dev), ttab=torch.zeros(S, device=dev, dtype=torch.long),
+                  idx=torch.zeros(1, device=dev, dtype=torch.int32), offsets=offsets,
+                  epsb=torch.empty(len(offsets), B, C, tile_size, tile_size, device=dev),
+                  tw=m._gaussian_weights(tile_size, tile_size, 1)[0, 0].contiguous(), context=context)
+        st["ptrs"] = torch.tensor([st["epsb"][k].data_ptr() for k in range(len(offsets))], dtype=torch.int64).to(dev)
+        if flows is not None:
+            st["flows"] = tuple(f.contiguous().clone() for f in flows)
+            st["masks"] = tuple(mk.reshape(num_clips, T1 - 1, h, w).contiguous().clone() for mk in masks)
+            st["ws"] = torch.empty(num_clips, T1 * C * h * w + 1, device=dev, dtype=torch.int64)
+        nf = getattr(m.model.diffusion_model, "num_frames", None)
+        whole = nf is not None and B == num_clips * nf
+        assert num_clips == 1 or whole, "num_clips > 1 needs clips of exactly num_frames frames"
+        per_call = max(1, int(m.unet_clips_per_call) // num_clips) if whole else 1
+
+        def step():
+            t_in = st["ttab"].index_select(0, st["idx"].long())
+            xb, scb = st["xb"], st["scb"]
+            tiles = [(xb[:, :, oy:oy + tile_size, ox:ox + tile_size], scb[:, :, oy:oy + tile_size, ox:ox + tile_size])
+                     for (ox, oy) in offsets]
+            for g0 in range(0, len(tiles), per_call):
+                grp = tiles[g0:g0 + per_call]
+                xi = torch.cat([a for a, _ in grp], 0) if len(grp) > 1 else grp[0][0].contiguous()
+                ci = torch.cat([b for _, b in grp], 0) if len(grp) > 1 else grp[0][1].contiguous()
+                eps = m._eps._eager(xi, ci, t_in, context)
+                for k, e in enumerate(eps.chunk(len(grp), 0)):
+                    st["epsb"][g0 + k].copy_(e)
+            if flows is None:
+                ops.canvas_posterior_dev_f32(xb, st["ptrs"], st["tw"], st["noise"], offsets, tile_size, st["coef"], st["idx"], xb)
+                return
+            ops.canvas_posterior_dev_f32(xb, st["ptrs"], st["tw"], st["noise"], offsets, tile_size, st["coef"], st["idx"],
+                                         st["lat"])
+            for k in range(num_clips):
+                ops.motion_guidance_dev_f32(st["lat"][k * T1:(k + 1) * T1], st["flows"][0][k], st["flows"][1][k],
+                                            st["masks"][0][k], st["masks"][1][k], st["ws"][k], xb[k * T1:(k + 1) * T1],
+                                            st["gstep"], st["idx"])
+
+        m.model.diffusion_model.kvc.get(ops, context)       # K/V of the (constant) context: computed outside the graph
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):                               # warm-up (lazy init, allocator); scribbles on xb: reloaded per run
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        n0 = ops.LAUNCHES[0]
+        with torch.cuda.graph(graph):
+            step()
+        st["graph"], st["n_kernels"] = graph, ops.LAUNCHES[0] - n0
+        self.cache[key] = st
+        return st
+
+    def run(self, x_T, struct_cond, context, flows, masks, guidance_scale, tile_size, tile_overlap, num_clips, S, t_of,
+            log_every_t, intermediates):
+        m = self.m
+        key = (tuple(x_T.shape), tile_size, tile_overlap, num_clips, flows is not None, id(context), context._version, S)
+        st = self.cache.get(key)
+        if st is None:
+            st = self._build(key, x_T, struct_cond, context, flows, masks, tile_size, tile_overlap, num_clips, S)
+        B, C, h, w = x_T.shape
+        T1 = B // num_clips
+        hh = m._h
+        coef = np.zeros((S, 5), dtype=np.float32)
+        for i in range(S):
+            coef[i] = (hh["sqrt_recip_alphas_cumprod"][i], hh["sqrt_recipm1_alphas_cumprod"][i], hh["posterior_mean_coef1"][i],
+                       hh["posterior_mean_coef2"][i],
+                       0.0 if i == 0 else np.exp(np.float32(0.5) * hh["posterior_log_variance_clipped"][i]))
+        st["coef"].copy_(torch.from_numpy(coef))
+        st["gstep"].copy_(torch.tensor([float(guidance_scale) * float(hh["posterior_log_variance_clipped"][i]) for i in range(S)],
+                                       dtype=torch.float32))
+        st["ttab"].copy_(torch.tensor([t_of(i) for i in range(S)], dtype=torch.long))
+        st["xb"].copy_(x_T)
+        st["scb"].copy_(struct_cond)
+        if flows is not None:
+            for dst, src in zip(st["flows"], flows):
+                dst.copy_(src)
+            for dst, src in zip(st["masks"], masks):
+                dst.copy_(src.reshape(dst.shape))
+        for i in reversed(range(S)):                         # noise_like draws in step order (same stream as per-step draws)
+            st["noise"][i] = torch.randn((T1, C, h, w), device=x_T.device)
+        for i in reversed(range(S)):
+            st["idx"].fill_(i)
+            st["graph"].replay()
+            m.ops.LAUNCHES[0] += st["n_kernels"]
+            if intermediates is not None and (i % log_every_t == 0 or i == S - 1):
+                intermediates.append(st["xb"].clone())
+        return st["xb"].clone()
+
+
 class LatentDiffusionVSRTextWT(_ModuleBase):
     def __init__(self, first_stage_config, cond_stage_config, structcond_stage_config, flownet_config=None,
                  num_frames=1, num_timesteps_cond=None, cond_stage_key="image", cond_stage_trainable=False,
@@ -226,6 +337,8 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
                                linear_start=linear_start, linear_end=linear_end, cosine_s=cosine_s)
         self.ori_timesteps = None
         self._eps = _EpsRunner(self, use_graph=use_cuda_graph)
+        self._steps = _StepRunner(self)
+        self.whole_step_graph = True      # one graph replay per DDPM step (tiles + posterior + guidance); False: eps-only graph
         self.unet_clips_per_call = 2      # clips (num_frames each) batched through one struct-encoder + UNet evaluation
         # struct encoder of step i-1 as a concurrent graph branch of step i (_EpsRunner._pipelined).  Correct (tests) but
         # measured neutral on a power-capped B200 (DDPM loop 772 -> 769 ms, profiles/r01_dev_run42*): off by default.
@@ -240,6 +353,7 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
         # captured graphs replay against the weight tensors they were captured with: new weights invalidate them
         self._eps.graphs.clear()
         self._eps.pipes.clear()
+        self._steps.clear()
         for prefix, mod in (("model.diffusion_model.", self.model.diffusion_model),
                             ("first_stage_model.", self.first_stage_model),
                             ("structcond_stage_model.", self.structcond_stage_model),
@@ -503,6 +617,15 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
         timesteps = self.num_timesteps if timesteps is None else timesteps
         if start_T is not None:
             timesteps = min(timesteps, start_T)
+        replaced = not (time_replace is None or time_replace == 1000)
+        if (self.whole_step_graph and self._eps.use_graph and img.is_cuda and not self.pipeline_struct_encoder
+                and callback is None and img_callback is None and hasattr(self.ops, "canvas_posterior_dev_f32")
+                and (flows is None or img.shape[0] // num_clips >= 2)):
+            t_of = (lambda k: self.ori_timesteps[k]) if replaced else (lambda k: k)
+            img = self._steps.run(img.contiguous(), struct_cond.contiguous(), self._context(cond), flows, masks,
+                                  guidance_scale, tile_size, tile_overlap, num_clips, timesteps, t_of, log_every_t,
+                                  intermediates if return_intermediates else None)
+            return (img, intermediates) if return_intermediates else img
         tile_weights = self._gaussian_weights(tile_size, tile_size, 1)
         for i in reversed(range(0, timesteps)):
             ts = torch.full((b,), i, device=device, dtype=torch.long)

@@ -106,7 +106,7 @@ def conv_gemm(a, w, *, taps=TAPS_1, a2=None, bias=None, epilogue=EPI_LINEAR, act
     d.groups = groups
     d.out, d.ldout, d.out_col0, d.out_f32 = out.data_ptr(), ldout, out_col0, int(out_f32)
     if stats_out is not None:
-        assert stats_out.dtype == torch.float64 and stats_out.shape == (T, stats_groups, 2) and stats_out.is_contiguous()
+        assert stats_out.dtype == torch.float64 and stats_out.shape == (T, stats_groups, 2, 2) and stats_out.is_contiguous()
         d.stats_out, d.stats_groups = stats_out.data_ptr(), stats_groups
     if SPLIT_K:
         need = _L.lib().mgld_conv_gemm_workspace_bytes(ctypes.byref(d))
@@ -233,6 +233,34 @@ def canvas_posterior_f32(x, eps_tiles, tile_w, noise, offsets, tile_size, c_reci
     return (out, eps_out) if want_eps else out
 
 
+def canvas_posterior_dev_f32(x, eps_ptrs, tile_w, noise_all, offsets, tile_size, coef_table, step_idx, out):
+    """graph-replayable canvas_posterior_f32: eps_ptrs = device int64 table of tile pointers (built once), per-step scalars
+    from coef_table[5*step_idx ..], noise slice noise_all[step_idx] (shape (T1,C,h,w), shared by the clips in x)."""
+    T, C, h, w = x.shape
+    n = len(offsets)
+    assert x.is_contiguous() and out.is_contiguous() and noise_all.is_contiguous() and eps_ptrs.numel() == n
+    assert coef_table.dtype == torch.float32 and step_idx.dtype == torch.int32 and tile_w.dtype == torch.float64
+    noise_tc = noise_all.shape[1] * noise_all.shape[2]
+    ox = (ctypes.c_int * n)(*[o[0] for o in offsets])
+    oy = (ctypes.c_int * n)(*[o[1] for o in offsets])
+    _count(1)
+    _L.check(_L.lib().mgld_canvas_posterior_dev_f32(
+        _L.ptr(x), _L.ptr(eps_ptrs), _L.ptr(tile_w), _L.ptr(noise_all), ctypes.c_longlong(noise_all.stride(0)), noise_tc,
+        _L.ptr(out), n, ox, oy, T * C, h, w, tile_size, _L.ptr(coef_table), _L.ptr(step_idx), _L.stream_ptr()))
+    return out
+
+
+def motion_guidance_dev_f32(latents, flow_fwd_prop, flow_bwd_prop, fwd_occ, bwd_occ, ws, out, step_table, step_idx):
+    """graph-replayable motion_guidance_f32: step = step_table[step_idx] read on the device; ws: int64 [numel + 1]"""
+    t, c, h, w = latents.shape
+    assert latents.is_contiguous() and out.is_contiguous() and ws.dtype == torch.int64 and ws.numel() >= latents.numel() + 1
+    _count(2)
+    _L.check(_L.lib().mgld_motion_guidance_dev_f32(_L.ptr(latents), _L.ptr(flow_fwd_prop), _L.ptr(flow_bwd_prop),
+                                                   _L.ptr(fwd_occ), _L.ptr(bwd_occ), _L.ptr(ws), _L.ptr(out),
+                                                   _L.ptr(step_table), _L.ptr(step_idx), t, c, h, w, _L.stream_ptr()))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # normalisation
 # ---------------------------------------------------------------------------------------------------------------
@@ -249,7 +277,7 @@ def _thwc(x):
 
 
 class _SumsPool:
-    """Zeroed fp64 [T, groups, 2] slots for the multi-pass GroupNorm statistics: ONE memset per forward (reset()) instead
+    """Zeroed [T, groups, 2] x 16-byte accumulator slots (mgld.h: fixed-point sums) for the multi-pass GroupNorm statistics: ONE memset per forward (reset()) instead
     of a zero-fill launch per normalisation.  A slot that was handed out since the last reset is zeroed on re-use.
     Buffers are kept per (T, groups, device) and never freed: captured CUDA graphs keep writing to their addresses."""
     SLOTS = 192
@@ -273,7 +301,7 @@ class _SumsPool:
         key = (T, groups, torch.device(device))
         ent = self.bufs.get(key)
         if ent is None:
-            ent = [torch.zeros(self.SLOTS, T, groups, 2, device=device, dtype=torch.float64), 0, [False] * self.SLOTS]
+            ent = [torch.zeros(self.SLOTS, T, groups, 2, 2, device=device, dtype=torch.float64), 0, [False] * self.SLOTS]
             self.bufs[key] = ent
         if ent[1] >= self.SLOTS:
             ent[1] = 0
@@ -305,7 +333,7 @@ def stats_pool_hold(on):
 
 
 def gn_stats(x1, x2=None, groups=32):
-    """-> double sums [T, groups, 2] over the virtual concat [x1 | x2] (NHWC fp16)."""
+    """-> fixed-point sums ([T, groups, 2] x 16 bytes, opaque) over the virtual concat [x1 | x2] (NHWC fp16)."""
     T, HW, C1, ld1 = _thwc(x1)
     C2, ld2 = (x2.shape[-1], x2.stride(-2)) if x2 is not None else (0, 0)
     sums = _sums_pool.get(T, groups, x1.device)
@@ -313,6 +341,12 @@ def gn_stats(x1, x2=None, groups=32):
     _L.check(_L.lib().mgld_gn_stats_f16(_L.ptr(x1), C1, ld1, _L.ptr(x2), C2, ld2, T, HW, groups, _L.ptr(sums),
                                         _L.stream_ptr()))
     return sums
+
+
+def decode_sums(sums):
+    """the opaque fixed-point accumulators of gn_stats ([..., 2] x 16 bytes) -> float64 (sum, sumsq) [..., 2] (tests/tools)"""
+    w = sums.contiguous().view(torch.int64)
+    return w[..., 0].double() + w[..., 1].double() * 2.0 ** -40
 
 
 def gn_finalize(sums, HW, C, eps):

@@ -85,7 +85,7 @@ class StatsPool:
         if not FUSE_GN_STATS:
             return
         if self.buf is None or self.buf.shape[1] != T or self.buf.device != torch.device(device):
-            self.buf = torch.zeros(self.slots, T, self.groups, 2, device=device, dtype=torch.float64)
+            self.buf = torch.zeros(self.slots, T, self.groups, 2, 2, device=device, dtype=torch.float64)
         else:
             self.buf.zero_()
         self.i = 0
