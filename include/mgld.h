@@ -255,6 +255,16 @@ int mgld_set_channels_f16(const float* src, void* dst, int b, int cs, int hw, in
 /* RAFT_SR.upsample_flow (:720-731): convex 8x upsampling, mask NHWC fp16 [b,h,w,576], flow (b,2,h,w) -> (b,2,8h,8w)     */
 int mgld_convex_upsample8_f32(const void* mask, const float* flow, float* out, int b, int h, int w, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * I/O edges on the GPU; frames stay device-resident between the decoder of the input and the encoder
+ * of the output.
+ * read_image (script :124-130) + F.interpolate(mode='bicubic') (:349-357) [+ clamp(-1,1) :376, + reflect pad right/bottom
+ * :383-387]: in uint8 [n, h, w, 3] -> out fp32 [n, 3, oh + pad_h, ow + pad_w].                                          */
+int mgld_frames_u8_to_f32_bicubic(const void* in, float* out, int n, int h, int w, int oh, int ow, int pad_h, int pad_w,
+                                  int clamp, void* stream);
+/* script :529-541: in fp32 [n, 3, h, w] in [0,1] -> out uint8 [n, crop_h, crop_w, 3] = (uint8)(x * 255), top-left crop     */
+int mgld_frames_f32_to_u8_hwc(const float* in, void* out, int n, int h, int w, int crop_h, int crop_w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,12 @@ class _AttnBlock:
         self.wv, self.bv = P.conv(p + ".v")
         self.wo, self.bo = P.conv(p + ".proj_out")
 
+    # bytes of fp32 scores per query panel.  The N x N score matrix of a frame never exists: queries are processed in panels
+    # of `rows` x N scores sized to stay resident in the 126 MB L2 between the three launches that touch them (QK^T GEMM ->
+    # row softmax -> PV GEMM), so HBM sees Q, K, V and O once instead of 829 MB of fp32 scores + 415 MB of fp16 P per frame
+    # at a 960x960 tile (N = 14400).
+    PANEL_BYTES = 32 << 20
+
     def __call__(self, ops, x):
         T, H, W, C = x.shape
         N = H * W
@@ -75,12 +81,15 @@ class _AttnBlock:
         q = ops.conv_gemm(xn, self.wq, bias=self.bq)
         k = ops.conv_gemm(xn, self.wk, bias=self.bk)
         o = torch.empty(T * N, C, device=x.device, dtype=torch.float16)
+        panel = max(128, min(N, (self.PANEL_BYTES // (4 * N)) // 128 * 128))
         for t in range(T):
-            rows = slice(t * N, (t + 1) * N)
-            s = ops.conv_gemm(q[rows], k[rows], out_f32=True)            # [N, N] fp32 scores
-            p = ops.softmax_rows(s, float(C) ** -0.5)                    # [N, N] fp16
-            vT = ops.conv_gemm(self.wv, xn[rows])                        # V^T = Wv Xn^T : [C, N]
-            ops.conv_gemm(p, vT, bias=self.bv, out=o[rows])              # P V + bv
+            vT = ops.conv_gemm(self.wv, xn[t * N:(t + 1) * N])           # V^T = Wv Xn^T : [C, N]
+            kt = k[t * N:(t + 1) * N]
+            for r0 in range(t * N, (t + 1) * N, panel):
+                rows = slice(r0, min(r0 + panel, (t + 1) * N))
+                s = ops.conv_gemm(q[rows], kt, out_f32=True)             # [panel, N] fp32 scores (L2-resident)
+                p = ops.softmax_rows(s, float(C) ** -0.5)                # [panel, N] fp16
+                ops.conv_gemm(p, vT, bias=self.bv, out=o[rows])          # P V + bv
         out = ops.conv_gemm(o, self.wo, bias=self.bo, res=x.reshape(T * N, C), beta=1.0)
         return out.reshape(T, H, W, C)
 

@@ -566,6 +566,33 @@ def axpby(x, y, a, b, relu=False):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# I/O edges (uint8 frames <-> the fp32 NCHW tensors of the path)
+# ---------------------------------------------------------------------------------------------------------------
+def frames_u8_to_f32_bicubic(frames_u8, oh, ow, pad_h=0, pad_w=0, clamp=False):
+    """uint8 [N,h,w,3] (HWC, as decoded from PNG) -> fp32 [N,3,oh+pad_h,ow+pad_w]: (x/255-0.5)/0.5, bicubic resize, optional
+    clamp(-1,1) and reflect pad (script :124-130, :349-357, :376, :383-387) in one launch"""
+    assert frames_u8.dtype == torch.uint8 and frames_u8.is_cuda and frames_u8.is_contiguous() and frames_u8.shape[-1] == 3
+    n, h, w, _ = frames_u8.shape
+    out = torch.empty(n, 3, oh + pad_h, ow + pad_w, device=frames_u8.device, dtype=torch.float32)
+    _count(1)
+    _L.check(_L.lib().mgld_frames_u8_to_f32_bicubic(_L.ptr(frames_u8), _L.ptr(out), n, h, w, oh, ow, pad_h, pad_w, int(clamp),
+                                                    _L.stream_ptr()))
+    return out
+
+
+def frames_f32_to_u8_hwc(frames, crop_h=None, crop_w=None):
+    """fp32 [N,3,H,W] in [0,1] -> uint8 [N,crop_h,crop_w,3] = (x*255).astype(uint8) of the top-left crop (script :529-541)"""
+    frames = _f32c(frames)
+    n, c, h, w = frames.shape
+    assert c == 3
+    ch, cw = crop_h or h, crop_w or w
+    out = torch.empty(n, ch, cw, 3, device=frames.device, dtype=torch.uint8)
+    _count(1)
+    _L.check(_L.lib().mgld_frames_f32_to_u8_hwc(_L.ptr(frames), _L.ptr(out), n, h, w, ch, cw, _L.stream_ptr()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # RAFT pieces
 # ---------------------------------------------------------------------------------------------------------------
 def conv_direct(x, w, bias, stride=1, pad=0, relu=False):

@@ -110,6 +110,8 @@ class VSRPipeline:
         self.S, self.n_frames, self.upscale = ddpm_steps, n_frames, upscale
         self.tile, self.stride, self.tile_overlap = vqgantile_size, vqgantile_stride, tile_overlap
         self.colorfix, self.seed, self.guidance_scale = colorfix_type, seed, guidance_scale
+        self.keep_latents = False                  # True: `last_latents` holds the sampled latents of every unit (see save_latents_npy)
+        self.last_latents = None
         self.clips_per_batch = clips_per_batch     # independent units (segments / VAE tiles) sampled in lock-step
         self.latent_tile = int(input_size / 8)     # script :450 tile_size=int(opt.input_size/8), --input_size 512
         if getattr(vq_model, "decoder", None) is not None:
@@ -128,6 +130,25 @@ class VSRPipeline:
         up = F.interpolate(frames, size=(int(frames.shape[-2] * self.upsample_scale),
                                          int(frames.shape[-1] * self.upsample_scale)), mode="bicubic")
         return [up[idx[i:i + self.n_frames]] for i in range(0, len(idx), self.n_frames)], n
+
+    def segments_from_u8(self, frames_u8):
+        """GPU-side input edge: uint8 HWC frames as decoded from the PNG files, (N,h,w,3) on the device ->
+        the same list of bicubic-upsampled segments `segments` returns, through ONE fused kernel (decode-normalise + bicubic)
+        instead of the reference's per-frame numpy / CPU-tensor work (script :124-130, :349-357)."""
+        n = frames_u8.shape[0]
+        idx = list(range(n))
+        while len(idx) % self.n_frames != 0:
+            idx.append(idx[-1])
+        h, w = frames_u8.shape[1:3]
+        self.upsample_scale = max(512 / min(h, w), self.upscale)
+        up = self.model.ops.frames_u8_to_f32_bicubic(frames_u8.contiguous(), int(h * self.upsample_scale),
+                                                     int(w * self.upsample_scale))
+        return [up[idx[i:i + self.n_frames]] for i in range(0, len(idx), self.n_frames)], n
+
+    def to_uint8(self, frames_sr):
+        """GPU-side output edge: (N,3,H,W) in [0,1] -> uint8 (N,H,W,3) exactly as the script writes its PNGs (x * 255
+        truncated, script :529-541), one fused kernel; this is what the clip all-gather moves."""
+        return self.model.ops.frames_f32_to_u8_hwc(frames_sr)
 
     def estimate_flows(self, im_lq_bs, flows_override=None):
         """script :392-416 -> flows [(T-1,2,h/8,w/8)] x2 (forward-prop, backward-prop), occlusion masks (T-1,1,h/8,w/8) x2"""
@@ -177,6 +198,7 @@ class VSRPipeline:
         `(b t)` batch; each unit's result is what it would be if it had been processed alone."""
         m = self.model
         out = [None] * len(units)
+        lat = [None] * len(units)
         todo = list(range(len(units)))
         while todo:
             shape0 = units[todo[0]][0].shape
@@ -199,6 +221,10 @@ class VSRPipeline:
                                       batch_size_sample=1, **({"num_clips": len(grp)} if len(grp) > 1 else {}))
             for k, i in enumerate(grp):
                 out[i] = self._finish_unit(samples[k * T:(k + 1) * T], units[i][0])
+                if self.keep_latents:
+                    lat[i] = samples[k * T:(k + 1) * T].clone()
+        if self.keep_latents:
+            self.last_latents = lat
         return out
 
     def _sr_tile(self, im_lq_pch, flow_f, flow_b, fwd_occ, bwd_occ, context):
@@ -274,7 +300,7 @@ class VSRPipeline:
 
     @torch.no_grad()
     def __call__(self, frames, context=None, flows_override=None, use_guidance=True, world_size=1, rank=0, group=None):
-        """frames (N,3,h,w) in [-1,1] on the model's device -> (N,3,H,W) in [0,1].
+        """frames (N,3,h,w) in [-1,1] — or uint8 (N,h,w,3) as decoded from PNG — on the model's device -> (N,3,H,W) in [0,1].
 
         world_size > 1 (one process per GPU, every rank holds the LR clip and calls this): ONE clip is sharded over the
         ranks at the granularity of its independent units (segment x VAE tile; SURVEY.md §8e axes 1 and 2) in contiguous
@@ -282,7 +308,7 @@ class VSRPipeline:
         exchanged with a single all-gather per tile shape; every rank assembles the whole clip."""
         if context is None:
             context = self.model.cond_stage_model([""])
-        segs, n = self.segments(frames)
+        segs, n = self.segments_from_u8(frames) if frames.dtype == torch.uint8 else self.segments(frames)
         metas = [self._segment_geometry(seg) for seg in segs]
         owner = [si for si, m in enumerate(metas) for _ in range(m["n_units"])]
         first = [0]
@@ -312,6 +338,23 @@ class VSRPipeline:
                 th, tw = min(self.tile, im.shape[2]), min(self.tile, im.shape[3])
                 shapes += [(im.shape[0], im.shape[1], th, tw)] * m["n_units"]
         return shapes
+
+
+def save_latents_npy(latents, out_dir, basenames):
+    """The latent dump of scripts/vsr_val_ddpm_text_T_vqganfin_w_latent.py:396-397: one `<basename>.npy` per frame holding the
+    sampled latent `samples[i]` as a (4, h, w) float32 array written with `np.save` (the consumer is the video-VAE training
+    data of the reference).  `latents`: (N, 4, h, w) tensor (e.g. torch.cat(pipe.last_latents) of an untiled clip)."""
+    import os
+    import numpy as np
+    os.makedirs(out_dir, exist_ok=True)
+    assert len(basenames) <= latents.shape[0]
+    paths = []
+    for i, name in enumerate(basenames):
+        path = os.path.join(out_dir, name + ".npy")
+        with open(path, "wb") as f:
+            np.save(f, latents[i].detach().float().cpu().numpy())
+        paths.append(path)
+    return paths
 
 
 def shard_units(num_units, world_size, rank):

@@ -343,3 +343,19 @@ def canvas_posterior_f32(x, eps_tiles, tile_w, noise, offsets, tile_size, c_reci
     mean = c1 * x0 + c2 * x
     out = mean + sigma * noise if noise is not None else mean
     return (out, eps) if want_eps else out
+
+
+def frames_u8_to_f32_bicubic(frames_u8, oh, ow, pad_h=0, pad_w=0, clamp=False):
+    x = (frames_u8.permute(0, 3, 1, 2).float() / 255.0 - 0.5) / 0.5
+    x = F.interpolate(x, size=(oh, ow), mode="bicubic")
+    if clamp:
+        x = x.clamp(-1.0, 1.0)
+    if pad_h or pad_w:
+        x = F.pad(x, (0, pad_w, 0, pad_h), mode="reflect")
+    return x
+
+
+def frames_f32_to_u8_hwc(frames, crop_h=None, crop_w=None):
+    n, c, h, w = frames.shape
+    x = (frames.permute(0, 2, 3, 1) * 255.0)[:, :crop_h or h, :crop_w or w]
+    return torch.from_numpy(x.cpu().numpy().astype("uint8")).to(frames.device)

@@ -108,3 +108,21 @@ def test_pipeline_tiled_segment_cut_and_assemble():
         assert len(units) == 2 and units[0][0].shape == (T, 3, 160, 160) and units[0][1].shape == (T - 1, 2, 20, 20)
         outs.append(pipe._segment_assemble(meta, pipe._sr_units(units, ctx)))
     assert outs[0].shape == (T, 3, H, W) and rel_err(outs[0], outs[1]) < 1e-5
+
+
+def test_latent_dump_format(tmp_path):
+    """`_w_latent` dump (scripts/vsr_val_ddpm_text_T_vqganfin_w_latent.py:396-397): per frame a (4,h,w) float32 .npy of the
+    sampled latent, readable with np.load, equal to what sample_canvas returned"""
+    import numpy as np
+    from mgld_vsr_b200.pipeline import save_latents_npy
+    ctx = det_tensor("ctx", (1, 77, 128))
+    pipe = _tiny_pipeline(1)
+    pipe.keep_latents = True
+    unit = (det_tensor("im_lat", (T, 3, 128, 160)).clamp(-1, 1), None, None, None, None)
+    pipe._sr_units([unit], ctx)
+    lat = torch.cat(pipe.last_latents, 0)
+    assert lat.shape == (T, 4, 16, 20)
+    paths = save_latents_npy(lat, str(tmp_path / "lat"), [f"{i:08d}" for i in range(T)])
+    for i, p in enumerate(paths):
+        a = np.load(p)
+        assert a.dtype == np.float32 and a.shape == (4, 16, 20) and np.array_equal(a, lat[i].numpy())

@@ -415,3 +415,24 @@ def test_raft_ops():
     assert torch.equal(O.set_channels(fl, buf1, 254), E.set_channels(fl, buf2, 254))
     mask = rnd(B, h, w, 576).half()
     assert rel_err(O.convex_upsample8(mask, fl), E.convex_upsample8(mask, fl)) < 1e-4
+
+
+@pytest.mark.parametrize("n,h,w,scale", [(3, 128, 128, 4.0), (2, 180, 320, 4.0), (2, 96, 150, 512 / 96), (1, 270, 480, 4.0)])
+def test_io_edges(n, h, w, scale):
+    """GPU-side I/O edges: read_image + bicubic (+ clamp + reflect pad) and the uint8 quantisation, against
+    the torch / numpy operations the reference script performs (script :124-130, :349-357, :376, :383-387, :529-541)"""
+    O = ops()
+    g = torch.Generator().manual_seed(n * h + w)
+    u8 = torch.randint(0, 256, (n, h, w, 3), generator=g, dtype=torch.uint8).to(DEV)
+    oh, ow = int(h * scale), int(w * scale)
+    ref = E.frames_u8_to_f32_bicubic(u8, oh, ow)
+    got = O.frames_u8_to_f32_bicubic(u8, oh, ow)
+    assert got.shape == ref.shape and (got - ref).abs().max() < 2e-5
+    ph, pw = ((oh // 32) + 1) * 32 - oh, ((ow // 32) + 1) * 32 - ow
+    ref = E.frames_u8_to_f32_bicubic(u8, oh, ow, ph, pw, clamp=True)
+    got = O.frames_u8_to_f32_bicubic(u8, oh, ow, ph, pw, clamp=True)
+    assert got.shape == ref.shape and (got - ref).abs().max() < 2e-5
+    sr = torch.rand(n, 3, oh + ph, ow + pw, generator=g).to(DEV)
+    sr[0, :, :4, :4] = torch.tensor([0.0, 1.0, 254.999 / 255, 0.5]).to(DEV)
+    assert torch.equal(O.frames_f32_to_u8_hwc(sr, oh, ow), E.frames_f32_to_u8_hwc(sr, oh, ow))
+    assert torch.equal(O.frames_f32_to_u8_hwc(sr), E.frames_f32_to_u8_hwc(sr))
