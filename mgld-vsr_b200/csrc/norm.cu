@@ -46,15 +46,15 @@ constexpr int kGnApplyItems = 1024;  // 8-channel vectors per block in gn_apply
 // order-independent fixed-point accumulation across blocks (fixsum_add, common.h).  `sums`: [T, G, 2] accumulators of two
 // 8-byte words each.
 __global__ void gn_stats_kernel(const __half* __restrict__ x1, int C1, int ld1, const __half* __restrict__ x2, int C2,
-                                int ld2, int HW, int G, double* __restrict__ sums) {
+                                int ld2, int HW, int G, double* __restrict__ sums, int rows_per_block) {
   pdl_launch_dependents();
   pdl_wait();
 
   extern __shared__ float sh[];  // [rpi * vpr][16]: per-thread (sum[8] | sumsq[8]) of its channel vector
   const int C = C1 + C2, vpr = C >> 3, cpg = C / G;
   const int t = blockIdx.y;
-  const int r0 = blockIdx.x * kGnRowsPerBlock;
-  const int rows = min(kGnRowsPerBlock, HW - r0);
+  const int r0 = blockIdx.x * rows_per_block;
+  const int rows = min(rows_per_block, HW - r0);
   // thread -> fixed channel vector, strided rows: per-channel fp32 partials stay in registers
   const int rpi = blockDim.x / vpr;  // rows handled per iteration (>= 1 because blockDim >= vpr)
   const int v = threadIdx.x % vpr, rr = threadIdx.x / vpr;
@@ -437,9 +437,17 @@ extern "C" int mgld_gn_stats_f16(const void* x1, int C1, int ld1, const void* x2
   MGLD_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0 && C % groups == 0 && C / 8 <= 704, "gn_stats: C1=%d C2=%d G=%d", C1, C2,
                  groups);
   MGLD_CHECK_ARG((C2 > 0) == (x2 != nullptr), "gn_stats: x2/C2 mismatch");
-  dim3 grid(ceil_div(HW, kGnRowsPerBlock), T);
+  // ~2 resident blocks per SM over all frames: long enough per block to keep 4 x 16-byte loads per thread in flight for
+  // many iterations (640 blocks of 64 rows were launch- / latency-bound at 1.6 TB/s on L2-resident maps), and few
+  // cross-block accumulations
+  int bpf = ceil_div(2 * num_sms(), T);
+  const int max_bpf = ceil_div(HW, kGnRowsPerBlock);
+  if (bpf > max_bpf) bpf = max_bpf;
+  if (bpf < 1) bpf = 1;
+  const int rpb = ceil_div(ceil_div(HW, bpf), 8) * 8;
+  dim3 grid(ceil_div(HW, rpb), T);
   MGLD_CUDA(launch_pdl(gn_stats_kernel, grid, dim3(gn_threads(C)), gn_threads(C) * 16 * sizeof(float), (cudaStream_t)stream,
-                       (const __half*)x1, C1, ld1 > 0 ? ld1 : C1, (const __half*)x2, C2, ld2 > 0 ? ld2 : C2, HW, groups, sums));
+                       (const __half*)x1, C1, ld1 > 0 ? ld1 : C1, (const __half*)x2, C2, ld2 > 0 ? ld2 : C2, HW, groups, sums, rpb));
   MGLD_LAUNCH_CHECK("gn_stats_kernel");
   return MGLD_OK;
 }

@@ -108,9 +108,13 @@ def test_pipeline_vs_reference_script_golden(name):
     for (x_T, samples), g in zip(units, gold["units"]):
         assert rel_err(x_T.cpu(), g["x_T"]) < 3e-3                      # LR latent (VAE encoder) + the shared noise stream
         # The golden run has 2 DDPM steps: its t=999 step turns eps into x0 with the factor sqrt(1/abar_999 - 1) = 14.6, so
-        # the latents have a range of +-70..160 (random-init nets) and carry the fp16 eps error times 14.6 — compared, like
-        # every network output, relative to their range (measured on B200: 2.4e-3 untiled, 3.5e-3 tiled).
-        assert rel_err(samples.cpu(), g["samples"]) < 6e-3, rel_err(samples.cpu(), g["samples"])
+        # the latents have a range of +-70..160 (random-init nets) and carry the fp16 eps error times 14.6, which the second
+        # network evaluation then sees as input.  Measured on B200 (tools/dev_e2e_debug2.py, teacher-forced): eps max error
+        # 3e-3..7e-3 of its range at t=999 (outlier activations |eps| ~ 10), mean 1e-4 of range -> latents: max error up to
+        # 1.3e-2 of their range, mean 1e-3 of their standard deviation.
+        d = (samples.cpu() - g["samples"]).abs()
+        assert d.max() / g["samples"].abs().max() < 2.5e-2, d.max() / g["samples"].abs().max()
+        assert d.mean() / g["samples"].std() < 2e-3, d.mean() / g["samples"].std()
     ok, stats = robust_close(F.avg_pool2d(sr, 4).cpu(), gold["sr_pool4"].float(), 2e-3, 1e-2)
     assert ok, stats
     ok, stats = robust_close(sr[:, :, 192:320, 224:352].cpu(), gold["sr_crop"].float(), 3e-3, 2e-2)
@@ -137,8 +141,16 @@ def test_pipeline_e2e_psnr_50_steps(flow_mode):
             ff = 1.5 * F.interpolate(det_tensor(f"e2e_ff{s_}", (T - 1, 2, 8, 8)), size=(64, 64), mode="bicubic").to(DEV)
             fb = -ff + 0.2 * F.interpolate(det_tensor(f"e2e_fb{s_}", (T - 1, 2, 8, 8)), size=(64, 64), mode="bicubic").to(DEV)
             flows.append((ff, fb))
+    used, orig_est = [], pipe.estimate_flows
+
+    def record(im, fo=None):
+        out = orig_est(im, fo)
+        used.append((out[0][0].clone(), out[0][1].clone(), out[1][0].clone(), out[1][1].clone()))
+        return out
+    pipe.estimate_flows = record
     with cpu_rng():
         sr = pipe(lr, context=ctx, flows_override=flows)
+    pipe.estimate_flows = orig_est
     assert sr.shape == (n, 3, 512, 512) and torch.isfinite(sr).all()
     # oracle pipeline, fp32 on the same GPU, same noise stream (the product re-seeds per unit: so does the oracle here)
     segs, _ = pipe.segments(lr)
@@ -147,12 +159,17 @@ def test_pipeline_e2e_psnr_50_steps(flow_mode):
         # oracle's RAFT); the oracle sampler is then driven by the SAME flow fields, so that a handful of occlusion-mask
         # pixels flipping at the threshold does not turn into a different (equally valid) 50-step trajectory.
         flows = []
-        for seg in segs:
+        for si, seg in enumerate(segs):
             fl, (fo, bo) = pipe.estimate_flows(seg.clamp(-1, 1))
+            for a, b in zip(used[si], (fl[0], fl[1], fo, bo)):
+                assert torch.equal(a, b)                      # RAFT (CUDA-graph replay) is repeatable call to call
             with torch.no_grad():
                 ofl, ofo, obo = PR.estimate_flows(sd, seg.clamp(-1, 1))
             assert rel_err(fl[0], ofl[0]) < 4e-3 and rel_err(fl[1], ofl[1]) < 4e-3
-            assert ((fo != ofo).float().mean() + (bo != obo).float().mean()).item() < 2e-3
+            mism = ((fo != ofo).float().mean() + (bo != obo).float().mean()).item()
+            print(f"[e2e raft] segment {si}: flow rel err {rel_err(fl[0], ofl[0]):.2e} / {rel_err(fl[1], ofl[1]):.2e}, "
+                  f"|flow| max {ofl[0].abs().max().item():.2f} px, occluded {ofo.mean().item():.3f}, mask mismatch {mism:.2e}")
+            assert mism < 2e-3
             flows.append((fl[0], fl[1]))
     rng = DeviceRng(42)
     outs = []
@@ -167,6 +184,8 @@ def test_pipeline_e2e_psnr_50_steps(flow_mode):
                                                 2.0 * F.interpolate(f1, scale_factor=2.0, mode="nearest")[None])
             outs.append(PR.sr_segment(sd, TINY_UNET, TINY_STRUCT, dd, vq_sd, dd, seg, ctx, rng, ddpm_steps=S, flow_fn=fn))
     ref = torch.cat(outs, 0)[:n]
+    per_frame = [round(psnr(sr[i:i + 1], ref[i:i + 1]), 1) for i in range(n)]
+    print(f"[e2e {flow_mode}] product vs oracle PSNR per frame: {per_frame}")
     p_got, p_ref = psnr(sr.cpu(), hr), psnr(ref.cpu(), hr)
     print(f"[e2e {flow_mode}] PSNR vs ground truth: product {p_got:.4f} dB, oracle {p_ref:.4f} dB; product vs oracle "
           f"{psnr(sr, ref):.2f} dB; mean |d| {(sr - ref).abs().mean().item():.2e}")
