@@ -904,293 +904,6 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }
 
 
-// =====================================================================================================================
-// v4 (head_dim 64): v3's pipeline (two ping-pong query tiles, S / P / O in separate TMEM columns, no row max after the
-// first key block) with TWO THREADS PER QUERY ROW: warps w and w+4 of a tile's eight softmax warps sit on the same TMEM
-// lane quadrant and take key columns [0,64) / [64,128) of the block.  What that buys (r01 ncu of v3: 168 registers with
-// spill reloads inside the loop, issue-slot utilisation 0.37, top stall = fixed-latency dependency):
-//   * 64 scores per thread fit the register file without spills (104 registers);
-//   * four softmax warps per scheduler instead of two: twice the warps to cover the FFMA2 -> MUFU -> FADD2 -> F2FP
-//     chains and the waits on PV(j-1) / S(j+1).
-// The two halves of a row agree on the reference maximum through shared memory: once at block 0 (row max), and through a
-// one-word "overflow" flag per warp pair per block (named barrier of 64 threads) for the fallback of the no-max path.
-// 640 threads: warps 0-3 = TMA, MMA, 2 idle (64 registers); warps 4-11 = tile 0, 12-19 = tile 1 (104 registers).
-// =====================================================================================================================
-constexpr int kV4Threads = 640;
-
-template <int kEmu>
-__global__ void __launch_bounds__(kV4Threads, 1)
-attention_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  constexpr int DH = 64;
-  constexpr int kTileBytes = 128 * DH * 2;
-  constexpr uint32_t kSCol = 0, kPCol = 256, kOCol = 384;
-
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t q_full, kv_full[kV2Stages], kv_empty[kV2Stages], s_full[2], s_free[2], p_full[2], pv_done[2];
-  __shared__ uint32_t tmem_base_slot;
-  __shared__ float xch_val[2][2][2][128];     // [tile][parity][half][row]: row max (block 0 / fallback), row sum (end)
-  __shared__ int xch_over[2][2][4][2];        // [tile][parity][quad][half]: "a row of this warp overflowed" flags
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem_base;
-  const uint32_t sKV = sQ + 2 * kTileBytes;
-
-  const int q0 = blockIdx.x * 256;
-  const int head = blockIdx.y, b = blockIdx.z;
-  const int nblk = (p.nkv + kKVTile - 1) / kKVTile;
-  const int kvb = p.kv_batched ? b : 0;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-    mbar_init(smem_u32(&q_full), 1);
-    for (int s = 0; s < kV2Stages; ++s) { mbar_init(smem_u32(&kv_full[s]), 1); mbar_init(smem_u32(&kv_empty[s]), 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&s_full[i]), 1);
-      mbar_init(smem_u32(&s_free[i]), 8);     // one arrival per softmax warp of the tile
-      mbar_init(smem_u32(&p_full[i]), 8);
-      mbar_init(smem_u32(&pv_done[i]), 1);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_slot;
-  pdl_launch_dependents();
-  pdl_wait();
-
-  if (warp < 4) {
-    setmaxnreg_dec<64>();
-    if (warp == 0) {
-      if (elect_one()) {
-        mbar_expect_tx(smem_u32(&q_full), 2 * kTileBytes);
-        tma_load_3d(sQ, &tmQ, smem_u32(&q_full), p.q_col0 + head * p.q_hstride, q0, b);
-        tma_load_3d(sQ + kTileBytes, &tmQ, smem_u32(&q_full), p.q_col0 + head * p.q_hstride, q0 + 128, b);
-        for (int j = 0; j < nblk; ++j) {
-          const int s = j % kV2Stages;
-          mbar_wait(smem_u32(&kv_empty[s]), ((j / kV2Stages) & 1) ^ 1);
-          const uint32_t fb = smem_u32(&kv_full[s]);
-          mbar_expect_tx(fb, 2 * kTileBytes);
-          tma_load_3d(sKV + s * 2 * kTileBytes, &tmK, fb, p.k_col0 + head * p.k_hstride, j * kKVTile, kvb);
-          tma_load_3d(sKV + s * 2 * kTileBytes + kTileBytes, &tmV, fb, p.v_col0 + head * p.v_hstride, j * kKVTile, kvb);
-        }
-      }
-    } else if (warp == 1) {
-      // issue loop: identical to v3 (warp-uniform state, only the tcgen05 instructions are predicated on the elected lane)
-      const bool leader = elect_one();
-      const uint32_t idesc_s = umma_idesc_f16(128, kKVTile, 0, 0);
-      const uint32_t idesc_o = umma_idesc_f16(128, DH, 0, 1);  // B = V, MN-major
-      const uint64_t dq = umma_smem_desc(sQ, 0, 1024, kSwz128);
-      const uint64_t dkv0 = umma_smem_desc(sKV, 0, 1024, kSwz128);
-      constexpr uint32_t kStageStep = (2 * kTileBytes) >> 4;
-      const uint32_t bar_sfull = smem_u32(&s_full[0]), bar_sfree = smem_u32(&s_free[0]), bar_pfull = smem_u32(&p_full[0]);
-      const uint32_t bar_pvdone = smem_u32(&pv_done[0]), bar_kvfull = smem_u32(&kv_full[0]), bar_kvempty = smem_u32(&kv_empty[0]);
-      const uint32_t ts = tmem_base + kSCol, tp = tmem_base + kPCol, to = tmem_base + kOCol;
-      auto issue_s = [&](const int i, const uint64_t dk) {
-        if (leader) {
-#pragma unroll
-          for (int k = 0; k < DH / 16; ++k)
-            umma_ss(ts + i * 128, dq + ((i * kTileBytes + k * 32) >> 4), dk + ((k * 32) >> 4), idesc_s, k != 0);
-          umma_commit(bar_sfull + 8 * i);
-        }
-      };
-      mbar_wait_poll(smem_u32(&q_full), 0);
-      mbar_wait_poll(bar_kvfull, 0);
-      tc_fence_after();
-      issue_s(0, dkv0);
-      issue_s(1, dkv0);
-      int st = 0, st_next = 1;
-      uint32_t ph_next = 0;
-      uint64_t dkv = dkv0;
-      uint64_t dkv_next = dkv0 + kStageStep;
-      uint32_t par = 0;
-      for (int j = 0; j < nblk; ++j) {
-        if (j + 1 < nblk) {
-          mbar_wait_poll(bar_kvfull + 8 * st_next, ph_next);
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            mbar_wait_poll(bar_sfree + 8 * i, par);
-            tc_fence_after();
-            issue_s(i, dkv_next);
-          }
-        }
-        const uint64_t dv = dkv + (kTileBytes >> 4);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          mbar_wait_poll(bar_pfull + 8 * i, par);
-          tc_fence_after();
-          if (leader) {
-#pragma unroll
-            for (int k = 0; k < kKVTile / 16; ++k)
-              umma_ts(to + i * 64, tp + i * 64 + k * 8, dv + ((k * 2048) >> 4), idesc_o, (j | k) != 0);
-            umma_commit(bar_pvdone + 8 * i);
-            if (i == 1) umma_commit(bar_kvempty + 8 * st);
-          }
-        }
-        par ^= 1;
-        st = st_next;
-        dkv = dkv_next;
-        if (++st_next == kV2Stages) { st_next = 0; ph_next ^= 1; dkv_next = dkv0; } else { dkv_next += kStageStep; }
-      }
-    }
-  } else {
-    setmaxnreg_inc<104>();
-    const int sw = warp - 4;
-    const int i = sw >> 3;                 // query tile
-    const int hf = (sw >> 2) & 1;          // key-column half of the block
-    const int quad = warp & 3;             // TMEM lane quadrant (== sw & 3 because 4 | 4)
-    const int row = quad * 32 + lane;
-    const uint32_t pair_bar = 1 + i * 4 + quad;          // named barrier of the two warps that share these 32 rows
-    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t srow = tmem_base + lane_off + kSCol + i * 128 + hf * 64;
-    const uint32_t prow = tmem_base + lane_off + kPCol + i * 64 + hf * 32;
-    const uint32_t orow = tmem_base + lane_off + kOCol + i * 64 + hf * 32;
-    const float k2 = p.scale_log2e;
-    float m_run = -INFINITY, l_run = 0.f;
-    float sc[64];
-    auto load_scores = [&](const int j) {
-      mbar_wait_poll(smem_u32(&s_full[i]), j & 1);
-      tc_fence_after();
-      tmem_ld_x32(srow, reinterpret_cast<uint32_t*>(sc));
-      tmem_ld_x32(srow + 32, reinterpret_cast<uint32_t*>(sc) + 32);
-    };
-    auto scores_loaded = [&]() {
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&s_free[i]));
-    };
-    auto block = [&](const int j, auto masked_tag, const bool has_next) {
-      constexpr bool kMasked = decltype(masked_tag)::value;
-      if constexpr (kMasked) {
-        const int kv_left = p.nkv - j * kKVTile - hf * 64;
-#pragma unroll
-        for (int u = 0; u < 64; ++u)
-          if (u >= kv_left) sc[u] = -INFINITY;
-      }
-      // row max over BOTH halves (exchange through shared memory, one 64-thread barrier)
-      auto row_max = [&]() {
-        float mx0 = fmaxf(sc[0], sc[1]), mx1 = fmaxf(sc[2], sc[3]);
-#pragma unroll
-        for (int u = 4; u < 64; u += 4) {
-          mx0 = fmaxf(mx0, fmaxf(sc[u], sc[u + 1]));
-          mx1 = fmaxf(mx1, fmaxf(sc[u + 2], sc[u + 3]));
-        }
-        const float mine = fmaxf(mx0, mx1);
-        xch_val[i][j & 1][hf][row] = mine;
-        named_bar_sync(pair_bar, 64);
-        return fmaxf(mine, xch_val[i][j & 1][hf ^ 1][row]);
-      };
-      auto rescale_o = [&](const float a) {           // this half's 32 of the 64 output columns
-#pragma unroll
-        for (int o0 = 0; o0 < 32; o0 += 16) {
-          uint32_t r[16];
-          tmem_ld_x16(orow + o0, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int u = 0; u < 16; ++u) r[u] = __float_as_uint(__uint_as_float(r[u]) * a);
-          tmem_st_x16(orow + o0, r);
-        }
-      };
-      float rs0 = 0.f, rs1 = 0.f;
-      auto exp_store = [&](const float nmk, const bool first_pass, const bool rescale, const float a) {
-        rs0 = 0.f; rs1 = 0.f;
-#pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 32) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int u = 0; u < 32; u += 2) {
-            float x0, x1, e0, e1;
-            ffma2(x0, x1, sc[c0 + u], sc[c0 + u + 1], k2, k2, nmk, nmk);
-            if (((u >> 1) & 3) < kEmu / 2) {
-              exp2_poly2(e0, e1, x0, x1);
-            } else {
-              e0 = ex2_approx(x0);
-              e1 = ex2_approx(x1);
-            }
-            fadd2(rs0, rs1, rs0, rs1, e0, e1);
-            pk[u >> 1] = pack_h2(e0, e1);
-          }
-          if (c0 == 0 && first_pass && j > 0) {
-            mbar_wait_poll(smem_u32(&pv_done[i]), (j - 1) & 1);
-            tc_fence_after();
-            if (__any_sync(0xffffffffu, rescale)) rescale_o(a);
-          }
-          tmem_st_x16(prow + (c0 >> 1), pk);
-        }
-      };
-      float alpha = 1.f;
-      if (!p.nomax || j == 0) {
-        const float mx = row_max();
-        const bool grow = (mx - m_run) * k2 > 8.f;
-        if (grow) {
-          alpha = ex2_approx((m_run - mx) * k2);
-          m_run = mx;
-        }
-        exp_store(-m_run * k2, true, grow, alpha);
-      } else {
-        exp_store(-m_run * k2, true, false, 1.f);
-        // each half keeps its partial row sum below 2^14, so the row sum stays below 2^15 and no exponential overflows fp16
-        const bool over = !(rs0 + rs1 < 16384.f);
-        const int w_over = __any_sync(0xffffffffu, over) ? 1 : 0;
-        if (lane == 0) xch_over[i][j & 1][quad][hf] = w_over;
-        named_bar_sync(pair_bar, 64);
-        if (w_over | xch_over[i][j & 1][quad][hf ^ 1]) {     // warp-pair uniform: both halves redo the block together
-          const float mx = row_max();
-          if (mx > m_run) {
-            alpha = ex2_approx((m_run - mx) * k2);
-            m_run = mx;
-          }
-          rescale_o(alpha);
-          exp_store(-m_run * k2, false, false, 1.f);
-        }
-      }
-      if (has_next) load_scores(j + 1);
-      tmem_st_wait();
-      l_run = l_run * alpha + (rs0 + rs1);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&p_full[i]));
-      if (has_next) scores_loaded();
-    };
-    const int nfull = p.nkv / kKVTile;
-    load_scores(0);
-    scores_loaded();
-    for (int j = 0; j < nfull; ++j) block(j, std::false_type{}, j + 1 < nblk);
-    if (nfull < nblk) block(nfull, std::true_type{}, false);
-    mbar_wait_poll(smem_u32(&pv_done[i]), (nblk - 1) & 1);
-    tc_fence_after();
-    xch_val[i][nblk & 1][hf][row] = l_run;               // parity nblk & 1: not the slot the last block's max may have used
-    named_bar_sync(pair_bar, 64);
-    const float inv = 1.f / (l_run + xch_val[i][nblk & 1][hf ^ 1][row]);
-    const int qi = q0 + i * 128 + row;
-    __half* optr = p.out + (static_cast<long long>(b) * p.nq + qi) * p.ldo + head * DH + hf * 32;
-    uint32_t r[32];
-    tmem_ld_x32(orow, r);
-    tmem_ld_wait();
-    if (qi < p.nq) {
-#pragma unroll
-      for (int u = 0; u < 32; u += 8) {
-        uint4 v;
-        v.x = pack_h2(__uint_as_float(r[u]) * inv, __uint_as_float(r[u + 1]) * inv);
-        v.y = pack_h2(__uint_as_float(r[u + 2]) * inv, __uint_as_float(r[u + 3]) * inv);
-        v.z = pack_h2(__uint_as_float(r[u + 4]) * inv, __uint_as_float(r[u + 5]) * inv);
-        v.w = pack_h2(__uint_as_float(r[u + 6]) * inv, __uint_as_float(r[u + 7]) * inv);
-        *reinterpret_cast<uint4*>(optr + u) = v;
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
 static long long* g_attn_dbg = nullptr;
 static bool nkv_blocks_for_stagger(int nkv) { return nkv > 4 * kKVTile; }   // pointless for a handful of key blocks
 
@@ -1252,19 +965,6 @@ static int launch_attention_v3(const mgld_attention_desc* d, cudaStream_t stream
     attr_set = true;
   }
   dim3 grid(ceil_div(d->nq, 256), d->heads, d->batch);
-  static int use_v4 = -1;   // MGLD_ATTN_V4=1: two threads per query row (attention_v4_kernel)
-  if (use_v4 < 0) { const char* e = getenv("MGLD_ATTN_V4"); use_v4 = e ? (atoi(e) != 0) : 0; }
-  if (use_v4 && !p.dbg) {
-    static const Fn kFns4[3] = {attention_v4_kernel<0>, attention_v4_kernel<2>, attention_v4_kernel<4>};
-    static bool attr4 = false;
-    if (!attr4) {
-      for (int i = 0; i < 3; ++i) MGLD_CUDA(cudaFuncSetAttribute(kFns4[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr4 = true;
-    }
-    MGLD_CUDA(launch_pdl(kFns4[attn_v3_emu() / 2], grid, dim3(kV4Threads), smem, stream, tmQ, tmK, tmV, p));
-    MGLD_LAUNCH_CHECK("attention_v4_kernel");
-    return MGLD_OK;
-  }
   MGLD_CUDA(launch_pdl(kFns[p.dbg ? 3 : attn_v3_emu() / 2], grid, dim3(kV3Threads), smem, stream, tmQ, tmK, tmV, p));
   MGLD_LAUNCH_CHECK("attention_v3_kernel");
   return MGLD_OK;

@@ -11,6 +11,7 @@ Everything that only depends on (LR latent, t) or on the constant text context i
 per context tensor).
 """
 import math
+import os
 from contextlib import contextmanager
 
 import numpy as np
@@ -338,7 +339,8 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
         self.ori_timesteps = None
         self._eps = _EpsRunner(self, use_graph=use_cuda_graph)
         self._steps = _StepRunner(self)
-        self.whole_step_graph = True      # one graph replay per DDPM step (tiles + posterior + guidance); False: eps-only graph
+        # one graph replay per DDPM step (tiles + posterior + guidance); False / MGLD_WHOLE_STEP=0: eps-only graph + eager tail
+        self.whole_step_graph = os.environ.get("MGLD_WHOLE_STEP", "1") != "0"
         self.unet_clips_per_call = 2      # clips (num_frames each) batched through one struct-encoder + UNet evaluation
         # struct encoder of step i-1 as a concurrent graph branch of step i (_EpsRunner._pipelined).  Correct (tests) but
         # measured neutral on a power-capped B200 (DDPM loop 772 -> 769 ms, profiles/r01_dev_run42*): off by default.
