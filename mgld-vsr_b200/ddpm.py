@@ -136,6 +136,7 @@ class _EpsRunner:
         graph, sx, ssc, st, out, n_kernels, _ = g
         sx.copy_(x); ssc.copy_(sc); st.copy_(t)
         graph.replay()
+        self.m.ops.stats_pool_mark_dirty()
         self.m.ops.LAUNCHES[0] += n_kernels          # kernels replayed by the graph
         return out.clone()
 
@@ -190,6 +191,7 @@ class _EpsRunner:
         P["st"].fill_(t_host)
         P["stn"].fill_(t_host if t_next_host is None else t_next_host)
         P["graphs"][cur].replay()
+        ops.stats_pool_mark_dirty()
         ops.LAUNCHES[0] += P["counts"][cur]
         P["have"], P["cur"] = (t_host if t_next_host is None else t_next_host), 1 - cur
         return P["outs"][cur].clone()
@@ -303,6 +305,7 @@ class _StepRunner:
             m.ops.LAUNCHES[0] += st["n_kernels"]
             if intermediates is not None and (i % log_every_t == 0 or i == S - 1):
                 intermediates.append(st["xb"].clone())
+        m.ops.stats_pool_mark_dirty()
         return st["xb"].clone()
 
 

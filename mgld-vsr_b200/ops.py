@@ -297,6 +297,14 @@ class _SumsPool:
                 ent[2] = [False] * self.SLOTS
             ent[1] = 0
 
+    def mark_dirty(self):
+        """A CUDA-graph replay wrote the slots it captured without going through get(): the Python-side flags no longer
+        describe the device.  Owners of captured graphs call this after every replay, so that the next eager forward's
+        reset() zeroes the buffers again.  (Found in r02: an eager forward whose key had last been used by a replayed graph
+        of ANOTHER forward accumulated onto that graph's sums - tests/test_ops_gpu.py::test_stats_pool_after_graph_replay.)"""
+        for ent in self.bufs.values():
+            ent[2] = [True] * self.SLOTS
+
     def get(self, T, groups, device):
         key = (T, groups, torch.device(device))
         ent = self.bufs.get(key)
@@ -307,7 +315,7 @@ class _SumsPool:
             ent[1] = 0
         i = ent[1]
         slot = ent[0][i]
-        if ent[2][i]:
+        if ent[2][i] or _POOL_ALWAYS_ZERO:
             slot.zero_()
             _count(1)
         ent[2][i] = True
@@ -315,12 +323,18 @@ class _SumsPool:
         return slot
 
 
+_POOL_ALWAYS_ZERO = os.environ.get("MGLD_POOL_ALWAYS_ZERO", "0") != "0"   # development: zero every slot when handed out
 _sums_pool = _SumsPool()
 
 
 def stats_pool_reset():
     """call at the start of a model forward (inside any CUDA-graph capture of it)"""
     _sums_pool.reset()
+
+
+def stats_pool_mark_dirty():
+    """call after replaying a CUDA graph that contains normalisation statistics (see _SumsPool.mark_dirty)"""
+    _sums_pool.mark_dirty()
 
 
 def stats_pool_hold(on):
@@ -717,5 +731,6 @@ class GraphedFn:
         for s_, x in zip(static, xs):
             s_.copy_(x)
         graph.replay()
+        stats_pool_mark_dirty()
         LAUNCHES[0] += n_kernels
         return out.clone()

@@ -10,10 +10,16 @@ the model classes and therefore through libmgld.so.  Shipped-script defects D2 (
 and D3 (VAE YAML path) are resolved the way the survey documents; quirks D10 (latent tile stride 750//8) and D13 (pad
 rule) are reproduced.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
 from .flow import forward_backward_consistency_check, resize_flow
+
+
+# development switch: VAE passes one unit at a time (the order of the reference script) instead of one (b t) batch per group
+_UNBATCHED_VAE = os.environ.get("MGLD_UNBATCHED_VAE", "0") != "0"
 
 
 class ImageSpliterTh:
@@ -172,25 +178,47 @@ class VSRPipeline:
     # ---- one unit of work = one VAE tile of one segment: script :428-473 --------------------------------------------
     def _prepare_unit(self, im_lq_pch):
         """script :428-440: re-seed, LR latent (struct cond) and the noised start x_T."""
-        m, T = self.model, im_lq_pch.shape[0]
-        torch.manual_seed(self.seed)                                              # seed_everything per tile (:428)
-        init_latent = m.get_first_stage_encoding(m.encode_first_stage(im_lq_pch))
-        # == randn_like(init_latent) of script :434 for the reference's contiguous NCHW latent, whatever our strides are
-        noise = torch.randn(init_latent.shape, device=init_latent.device, dtype=init_latent.dtype)
-        t = torch.full((T,), 999, device=im_lq_pch.device, dtype=torch.long)
-        x_T = m.q_sample_respace(x_start=init_latent, t=t, sqrt_alphas_cumprod=self.sqrt_ac,
-                                 sqrt_one_minus_alphas_cumprod=self.sqrt_1m_ac, noise=noise)
-        return init_latent, x_T
+        return self._prepare_units([im_lq_pch])[0]
+
+    def _prepare_units(self, ims):
+        """script :428-440 for several units of equal shape: ONE AutoencoderKL.encode over all their frames (the encoder is
+        per-frame), then per unit exactly the script's sequence — re-seed, posterior sample, x_T noise."""
+        m, T = self.model, ims[0].shape[0]
+        from .autoencoder import DiagonalGaussianDistribution
+        post = m.encode_first_stage(ims[0] if len(ims) == 1 else torch.cat(ims, 0))
+        out = []
+        for k in range(len(ims)):
+            torch.manual_seed(self.seed)                                          # seed_everything per tile (:428)
+            pk = post if len(ims) == 1 else DiagonalGaussianDistribution(post.parameters[k * T:(k + 1) * T], post.ops)
+            init_latent = m.get_first_stage_encoding(pk)
+            # == randn_like(init_latent) of script :434 for the reference's contiguous NCHW latent, whatever our strides are
+            noise = torch.randn(init_latent.shape, device=init_latent.device, dtype=init_latent.dtype)
+            t = torch.full((T,), 999, device=init_latent.device, dtype=torch.long)
+            x_T = m.q_sample_respace(x_start=init_latent, t=t, sqrt_alphas_cumprod=self.sqrt_ac,
+                                     sqrt_one_minus_alphas_cumprod=self.sqrt_1m_ac, noise=noise)
+            out.append((init_latent, x_T))
+        return out
 
     def _finish_unit(self, samples, im_lq_pch):
         """script :465-473: temporal VAE decode with the LR encoder taps, colour fix."""
-        _, enc_fea = self.vq.encode(im_lq_pch)
+        return self._finish_units(samples, [im_lq_pch])[0]
+
+    def _finish_units(self, samples, ims):
+        """script :465-473 for several units of equal shape in one (b t) batch: video-VAE encode (feature taps) and temporal
+        decode are per-frame except the temporal mixing layers, which split the batch into clips of num_frames; AdaIN /
+        wavelet statistics are per frame."""
+        T, K = ims[0].shape[0], len(ims)
+        nf = self.vq.dd.get("num_frames") if hasattr(self.vq, "dd") else None
+        if K > 1 and nf != T:                      # the temporal layers can only split whole clips of num_frames
+            return [self._finish_units(samples[k * T:(k + 1) * T], [ims[k]])[0] for k in range(K)]
+        im = ims[0] if K == 1 else torch.cat(ims, 0)
+        _, enc_fea = self.vq.encode(im)
         x = self.vq.decode(samples * (1.0 / self.model.scale_factor), enc_fea)
         if self.colorfix == "adain":
-            x = adaptive_instance_normalization(x, im_lq_pch)
+            x = adaptive_instance_normalization(x, im)
         elif self.colorfix == "wavelet":
-            x = wavelet_reconstruction(x, im_lq_pch)
-        return x
+            x = wavelet_reconstruction(x, im)
+        return list(x.chunk(K, 0)) if K > 1 else [x]
 
     def _sr_units(self, units, context):
         """units: [(im_lq_pch, flow_f, flow_b, fwd_occ, bwd_occ)] -> [decoded tile].  Units are independent (the script
@@ -207,7 +235,10 @@ class VSRPipeline:
             grp = grp[:max(1, self.clips_per_batch)]
             todo = [i for i in todo if i not in grp]
             T = shape0[0]
-            prep = [self._prepare_unit(units[i][0]) for i in grp]
+            if _UNBATCHED_VAE:
+                prep = [self._prepare_unit(units[i][0]) for i in grp]
+            else:
+                prep = self._prepare_units([units[i][0] for i in grp])
             init_latent = torch.cat([p[0] for p in prep], 0)
             x_T = torch.cat([p[1] for p in prep], 0)
             if has_flow0:
@@ -219,8 +250,10 @@ class VSRPipeline:
                                       flows=flows, masks=masks, batch_size=T, timesteps=self.S, time_replace=self.S,
                                       x_T=x_T, tile_size=self.latent_tile, tile_overlap=self.tile_overlap,
                                       batch_size_sample=1, **({"num_clips": len(grp)} if len(grp) > 1 else {}))
-            for k, i in enumerate(grp):
-                out[i] = self._finish_unit(samples[k * T:(k + 1) * T], units[i][0])
+            fin = [self._finish_unit(samples[k * T:(k + 1) * T], units[i][0]) for k, i in enumerate(grp)] if _UNBATCHED_VAE \
+                else self._finish_units(samples, [units[i][0] for i in grp])
+            for k, (i, x) in enumerate(zip(grp, fin)):
+                out[i] = x
                 if self.keep_latents:
                     lat[i] = samples[k * T:(k + 1) * T].clone()
         if self.keep_latents:

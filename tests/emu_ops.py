@@ -120,6 +120,10 @@ def stats_pool_reset():
     pass
 
 
+def stats_pool_mark_dirty():
+    pass
+
+
 def gn_stats(x1, x2=None, groups=32):
     x = _cat(x1, x2).double()
     T, C = x.shape[0], x.shape[-1]

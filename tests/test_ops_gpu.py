@@ -436,3 +436,26 @@ def test_io_edges(n, h, w, scale):
     sr[0, :, :4, :4] = torch.tensor([0.0, 1.0, 254.999 / 255, 0.5]).to(DEV)
     assert torch.equal(O.frames_f32_to_u8_hwc(sr, oh, ow), E.frames_f32_to_u8_hwc(sr, oh, ow))
     assert torch.equal(O.frames_f32_to_u8_hwc(sr), E.frames_f32_to_u8_hwc(sr))
+
+
+def test_stats_pool_after_graph_replay():
+    """Regression (r02): the pooled GroupNorm accumulators are zeroed lazily by Python-side dirty flags; a CUDA-graph REPLAY
+    writes its slots without touching the flags.  An eager forward that was the first user of a key after (i) an eager
+    reset had cleared the flags and (ii) a replayed graph of another forward had written the key's slots accumulated onto
+    stale sums (first unit of a clip wrong after a VAE-tiled clip had been processed).  Graph owners now mark the pool dirty
+    after every replay."""
+    O = ops()
+    x, y = (rnd(4, 1024, 64) + 0.3).half(), (rnd(2, 1024, 64, seed=5) - 0.2).half()
+    g, b = rnd(64), rnd(64, seed=2)
+
+    def forward(t):                       # what a model forward does: one reset, then its normalisations
+        O.stats_pool_reset()
+        return O.group_norm(t, g, b, 1e-5, True)
+    ref = E.group_norm(x, g, b, 1e-5, True)
+    assert rel_err(forward(x), ref) < 3e-3
+    f = O.GraphedFn(forward)
+    assert rel_err(f(x), ref) < 3e-3      # warm-up + capture + replay
+    forward(y)                            # an eager forward on another key: its reset() clears every flag
+    assert rel_err(f(x), ref) < 3e-3      # replay: the device slots of x's key are written, Python flags are not
+    assert rel_err(forward(x), ref) < 3e-3, "eager forward accumulated onto the sums left by a graph replay"
+    assert rel_err(forward(x), ref) < 3e-3
