@@ -330,6 +330,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="override the clip length (development)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the second (host-buffer) timed pass (long single-GPU runs of configs 4/5)")
     ap.add_argument("--flow", default="raft", choices=["raft", "synthetic"],
                     help="raft: RAFT_SR flow estimation inside the timed path (the reference's behaviour); synthetic: given flows")
     args = ap.parse_args()
@@ -441,21 +442,21 @@ def main():
         sr_ = run_clip(d)
         if out_host is not None:          # strong-scaled clip: every rank uploads the LR clip, rank 0 reads the result back
             out_host.copy_(sr_, non_blocking=True)
-    if args.config in (2, 3):
+    if args.config in (2, 3) and not args.no_e2e:
         e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    ms_e2e = timed(e2e_step, args.steps) if not args.no_e2e else None
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
     frames_total = n_frames * (world if seq_sharding else 1)
     value = frames_total * args.steps / (ms / 1e3)
-    e2e_value = frames_total * args.steps / (ms_e2e / 1e3)
+    e2e_value = frames_total * args.steps / (ms_e2e / 1e3) if ms_e2e else None
     line = {"metric": C["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if seq_sharding else "strong",
             "vs_baseline": None, "dtype": "f16 (fp32 accumulate; fp32 norms/softmax/schedule/guidance)", "data": "synthetic",
             "config": workload_config(args, world), "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": clip_host.numel() * 4,
-                    "d2h_bytes_per_step": n_frames * 3 * H * W * 4, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": n_frames * 3 * H * W * 4, "ms_per_step": ms_e2e / args.steps if ms_e2e else None},
             "gpu_launches": launches}
     if rank == 0:
         # ---- the other half of the BASELINE metric + rooflines of the two tensor-core kernels ------------------------------
