@@ -905,313 +905,6 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 
 
-// =====================================================================================================================
-// v5 (head_dim 64): 64-key blocks with DOUBLE-BUFFERED S and P.
-// v3's role counters (profiles/r01_dev_run31*) put ~500 of the ~3160 cycles of a 128-key block pair into waiting for
-// PV(j-1) before P(j) may be stored, and the MMA warp idles ~1300 cycles per block waiting for P: with one P buffer per
-// tile (S0 S1 | P0 P1 | O0 O1 fill the 512 TMEM columns at 128-key blocks) the softmax and the tensor core hand a single
-// token back and forth.  Halving the key block halves S and P, so both fit twice:
-//     S[tile][buf] 4 x 64 columns [0,256) | P[tile][buf] 4 x 32 columns [256,384) | O[tile] 2 x 64 columns [384,512)
-// * S(j+2) is issued as soon as the softmax warps hold S(j) in registers, PV(j) as soon as P(j) is stored: the softmax of a
-//   tile never waits for an MMA of the SAME block - P(j) goes to the buffer PV(j-2) read, which finished a block ago;
-// * a thread holds 64 scores (no spills; the 128-score row of v3 needed ~205 registers);
-// * same numerics as v3: exp2 domain, no row max after block 0 (overflow-checked fallback), lazy rescale, P in fp16, row
-//   sum over the unrounded fp32 probabilities, 2 of 8 exponentials on the FMA pipe.
-// Roles as in v3 (384 threads: TMA warp, MMA warp, 2 idle, 2 x 4 softmax warps, thread == query row); K/V stages hold one
-// 64-key K tile + V tile (16 KB), six of them.
-// =====================================================================================================================
-constexpr int kV5Keys = 64;
-constexpr int kV5Stages = 6;
-
-template <int kEmu>
-__global__ void __launch_bounds__(kV3Threads, 1)
-attention_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  constexpr int DH = 64;
-  constexpr int kQBytes = 128 * DH * 2;        // 16 KB: one [128 x 64] query tile
-  constexpr int kKBytes = kV5Keys * DH * 2;    // 8 KB: one [64 x 64] K or V tile
-  constexpr uint32_t kSCol = 0, kPCol = 256, kOCol = 384;
-
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t q_full, kv_full[kV5Stages], kv_empty[kV5Stages], s_full[2][2], s_free[2][2], p_full[2][2],
-      pv_done[2][2];
-  __shared__ uint32_t tmem_base_slot;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem_base;
-  const uint32_t sKV = sQ + 2 * kQBytes;       // stage s: K at + s * 2 * kKBytes, V after K
-
-  const int q0 = blockIdx.x * 256;
-  const int head = blockIdx.y, b = blockIdx.z;
-  const int nblk = (p.nkv + kV5Keys - 1) / kV5Keys;
-  const int kvb = p.kv_batched ? b : 0;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-    mbar_init(smem_u32(&q_full), 1);
-    for (int s = 0; s < kV5Stages; ++s) { mbar_init(smem_u32(&kv_full[s]), 1); mbar_init(smem_u32(&kv_empty[s]), 1); }
-    for (int i = 0; i < 2; ++i)
-      for (int u = 0; u < 2; ++u) {
-        mbar_init(smem_u32(&s_full[i][u]), 1);
-        mbar_init(smem_u32(&s_free[i][u]), 4);    // one arrival per softmax warp
-        mbar_init(smem_u32(&p_full[i][u]), 4);
-        mbar_init(smem_u32(&pv_done[i][u]), 1);
-      }
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_slot;
-  pdl_launch_dependents();
-  pdl_wait();
-
-  if (warp < 4) {
-    setmaxnreg_dec<88>();
-    if (warp == 0) {
-      if (elect_one()) {
-        mbar_expect_tx(smem_u32(&q_full), 2 * kQBytes);
-        tma_load_3d(sQ, &tmQ, smem_u32(&q_full), p.q_col0 + head * p.q_hstride, q0, b);
-        tma_load_3d(sQ + kQBytes, &tmQ, smem_u32(&q_full), p.q_col0 + head * p.q_hstride, q0 + 128, b);
-        int s = 0;
-        uint32_t ph = 0;
-        for (int j = 0; j < nblk; ++j) {
-          mbar_wait(smem_u32(&kv_empty[s]), ph ^ 1);
-          const uint32_t fb = smem_u32(&kv_full[s]);
-          mbar_expect_tx(fb, 2 * kKBytes);
-          tma_load_3d(sKV + s * 2 * kKBytes, &tmK, fb, p.k_col0 + head * p.k_hstride, j * kV5Keys, kvb);
-          tma_load_3d(sKV + s * 2 * kKBytes + kKBytes, &tmV, fb, p.v_col0 + head * p.v_hstride, j * kV5Keys, kvb);
-          if (++s == kV5Stages) { s = 0; ph ^= 1; }
-        }
-      }
-    } else if (warp == 1) {
-      // Issue loop (warp-uniform state; only the tcgen05 instructions are predicated on the elected lane, see v3).
-      const bool leader = elect_one();
-      const uint32_t idesc_s = umma_idesc_f16(128, kV5Keys, 0, 0);
-      const uint32_t idesc_o = umma_idesc_f16(128, DH, 0, 1);  // B = V, MN-major
-      const uint64_t dq = umma_smem_desc(sQ, 0, 1024, kSwz128);
-      const uint64_t dkv0 = umma_smem_desc(sKV, 0, 1024, kSwz128);
-      constexpr uint32_t kStageStep = (2 * kKBytes) >> 4;
-      const uint32_t bar_sfull = smem_u32(&s_full[0][0]), bar_sfree = smem_u32(&s_free[0][0]), bar_pfull = smem_u32(&p_full[0][0]);
-      const uint32_t bar_pvdone = smem_u32(&pv_done[0][0]), bar_kvfull = smem_u32(&kv_full[0]), bar_kvempty = smem_u32(&kv_empty[0]);
-      const uint32_t ts = tmem_base + kSCol, tp = tmem_base + kPCol, to = tmem_base + kOCol;
-      // S_i(block) -> S buffer u of tile i; dk = descriptor of the block's K tile
-      auto issue_s = [&](const int i, const int u, const uint64_t dk) {
-        if (leader) {
-#pragma unroll
-          for (int k = 0; k < DH / 16; ++k)
-            umma_ss(ts + (i * 2 + u) * 64, dq + ((i * kQBytes + k * 32) >> 4), dk + ((k * 32) >> 4), idesc_s, k != 0);
-          umma_commit(bar_sfull + 8 * (i * 2 + u));
-        }
-      };
-      mbar_wait_poll(smem_u32(&q_full), 0);
-      mbar_wait_poll(bar_kvfull, 0);
-      tc_fence_after();
-      issue_s(0, 0, dkv0);
-      issue_s(1, 0, dkv0);
-      if (nblk > 1) {
-        mbar_wait_poll(bar_kvfull + 8, 0);
-        tc_fence_after();
-        issue_s(0, 1, dkv0 + kStageStep);
-        issue_s(1, 1, dkv0 + kStageStep);
-      }
-      int st = 0;                     // stage of block j
-      int st2 = 2 % kV5Stages;        // stage of block j + 2
-      uint32_t ph2 = 0;               // kv_full parity of block j + 2
-      for (int j = 0; j < nblk; ++j) {
-        const int u = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        const uint64_t dv = dkv0 + st * kStageStep + (kKBytes >> 4);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          mbar_wait_poll(bar_pfull + 8 * (i * 2 + u), ph);
-          tc_fence_after();
-          if (leader) {
-#pragma unroll
-            for (int k = 0; k < kV5Keys / 16; ++k)   // A: 16 keys = 8 packed columns per step; B: 16 key rows = 2048 B
-              umma_ts(to + i * 64, tp + (i * 2 + u) * 32 + k * 8, dv + ((k * 2048) >> 4), idesc_o, (j | k) != 0);
-            umma_commit(bar_pvdone + 8 * (i * 2 + u));
-            if (i == 1) umma_commit(bar_kvempty + 8 * st);
-          }
-        }
-        if (j + 2 < nblk) {
-          mbar_wait_poll(bar_kvfull + 8 * st2, ph2);
-          const uint64_t dk2 = dkv0 + st2 * kStageStep;
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            mbar_wait_poll(bar_sfree + 8 * (i * 2 + u), ph);   // softmax_i holds S_i(j) in registers: buffer u is free
-            tc_fence_after();
-            issue_s(i, u, dk2);
-          }
-        }
-        if (++st == kV5Stages) st = 0;
-        if (++st2 == kV5Stages) { st2 = 0; ph2 ^= 1; }
-      }
-    }
-  } else {
-    // softmax warpgroup i: warps 4-7 -> tile 0, warps 8-11 -> tile 1; thread == query row
-    setmaxnreg_inc<208>();
-    const int i = (warp - 4) >> 2;
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t srow0 = tmem_base + lane_off + kSCol + i * 128;   // + u * 64
-    const uint32_t prow0 = tmem_base + lane_off + kPCol + i * 64;    // + u * 32
-    const uint32_t orow = tmem_base + lane_off + kOCol + i * 64;
-    const uint32_t bar_sfull = smem_u32(&s_full[i][0]), bar_sfree = smem_u32(&s_free[i][0]), bar_pfull = smem_u32(&p_full[i][0]);
-    const uint32_t bar_pvdone = smem_u32(&pv_done[i][0]);
-    const float k2 = p.scale_log2e;
-    float m_run = -INFINITY, l_run = 0.f;
-    // Two register buffers of 64 scores: the TMEM load of S(j+1) is issued as soon as S(j) has arrived and runs while
-    // block j is being exponentiated.  TMEM reads are the scarce resource of this kernel: 64 KB of fp32 scores per
-    // 128 x 128 block at the ~64 B/clk/SM the load path sustains (B300_MICROARCH.md; conv_gemm's epilogue sees the same
-    // rate) is 1024 cycles per tile, 2048 per tile pair - more than the 1536 MUFU cycles - so they must never be exposed.
-    float scA[kV5Keys], scB[kV5Keys];
-    auto rescale_o = [&](const float a) {
-#pragma unroll
-      for (int o0 = 0; o0 < DH; o0 += 16) {
-        uint32_t r[16];
-        tmem_ld_x16(orow + o0, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int u = 0; u < 16; ++u) r[u] = __float_as_uint(__uint_as_float(r[u]) * a);
-        tmem_st_x16(orow + o0, r);
-      }
-    };
-    auto load_scores = [&](const int j, float* dst) {     // asynchronous: completed by the next tmem_ld_wait()
-      const int u = j & 1;
-      mbar_wait_poll(bar_sfull + 8 * u, (j >> 1) & 1);
-      tc_fence_after();
-      tmem_ld_x32(srow0 + u * 64, reinterpret_cast<uint32_t*>(dst));
-      tmem_ld_x32(srow0 + u * 64 + 32, reinterpret_cast<uint32_t*>(dst) + 32);
-    };
-    // block j: its scores are in flight into `sc`; `nxt` receives S(j+1)
-    auto block = [&](const int j, auto masked_tag, float* sc, float* nxt, const bool has_next) {
-      constexpr bool kMasked = decltype(masked_tag)::value;
-      const int u = j & 1;
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_sfree + 8 * u);          // S buffer u may take S(j + 2)
-      if (has_next) load_scores(j + 1, nxt);
-      if constexpr (kMasked) {
-        const int kv_left = p.nkv - j * kV5Keys;
-#pragma unroll
-        for (int c = 0; c < kV5Keys; ++c)
-          if (c >= kv_left) sc[c] = -INFINITY;
-      }
-      auto row_max = [&]() {
-        float mx0 = fmaxf(sc[0], sc[1]), mx1 = fmaxf(sc[2], sc[3]);
-#pragma unroll
-        for (int c = 4; c < kV5Keys; c += 4) {
-          mx0 = fmaxf(mx0, fmaxf(sc[c], sc[c + 1]));
-          mx1 = fmaxf(mx1, fmaxf(sc[c + 2], sc[c + 3]));
-        }
-        return fmaxf(mx0, mx1);
-      };
-      uint32_t pk[kV5Keys / 2];
-      float rs0 = 0.f, rs1 = 0.f;
-      auto exps = [&](const float nmk) {
-        rs0 = 0.f; rs1 = 0.f;
-#pragma unroll
-        for (int c = 0; c < kV5Keys; c += 2) {
-          float x0, x1, e0, e1;
-          ffma2(x0, x1, sc[c], sc[c + 1], k2, k2, nmk, nmk);
-          if (((c >> 1) & 3) < kEmu / 2) {          // kEmu of every 8 exponentials on the FMA pipe
-            exp2_poly2(e0, e1, x0, x1);
-          } else {
-            e0 = ex2_approx(x0);
-            e1 = ex2_approx(x1);
-          }
-          fadd2(rs0, rs1, rs0, rs1, e0, e1);
-          pk[c >> 1] = pack_h2(e0, e1);
-        }
-      };
-      // O may only be touched once every PV issued so far is complete: PV(j-1) (and, being older, PV(j-2)).  The rescale
-      // also waits for the prefetched scores (tcgen05.wait::ld covers every outstanding load) - it is the rare path.
-      auto wait_all_pv = [&]() {
-        if (j >= 1) { mbar_wait_poll(bar_pvdone + 8 * (u ^ 1), ((j - 1) >> 1) & 1); tc_fence_after(); }
-      };
-      float alpha = 1.f;
-      if (!p.nomax || j == 0) {
-        const float mx = row_max();
-        const bool grow = (mx - m_run) * k2 > 8.f;   // lazy: only move the reference when it grew by more than 2^8
-        if (grow) {
-          alpha = ex2_approx((m_run - mx) * k2);      // 0 on the first block
-          m_run = mx;
-        }
-        exps(-m_run * k2);
-        if (j > 0 && __any_sync(0xffffffffu, grow)) { wait_all_pv(); rescale_o(alpha); }
-      } else {
-        exps(-m_run * k2);
-        const bool over = !(rs0 + rs1 < 32768.f);     // see v3: bounds every exponential of the block below fp16 overflow
-        if (__any_sync(0xffffffffu, over)) {
-          const float mx = row_max();
-          if (mx > m_run) {
-            alpha = ex2_approx((m_run - mx) * k2);
-            m_run = mx;
-          }
-          wait_all_pv();
-          rescale_o(alpha);
-          exps(-m_run * k2);
-        }
-      }
-      // P buffer u was last read by PV(j - 2)
-      if (j >= 2) { mbar_wait_poll(bar_pvdone + 8 * u, ((j >> 1) - 1) & 1); tc_fence_after(); }
-      tmem_st_x16(prow0 + u * 32, pk);
-      tmem_st_x16(prow0 + u * 32 + 16, pk + 16);
-      tmem_st_wait();
-      l_run = l_run * alpha + (rs0 + rs1);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_pfull + 8 * u);
-    };
-    const int nfull = p.nkv / kV5Keys;
-    load_scores(0, scA);
-    int j = 0;
-    for (; j + 1 < nfull; j += 2) {                       // two blocks per iteration: the register buffers swap roles
-      block(j, std::false_type{}, scA, scB, true);
-      block(j + 1, std::false_type{}, scB, scA, j + 2 < nblk);
-    }
-    if (j < nfull) {                                       // odd number of full blocks: one more from buffer A
-      block(j, std::false_type{}, scA, scB, j + 1 < nblk);
-      if (j + 1 < nblk) block(j + 1, std::true_type{}, scB, scA, false);
-    } else if (j < nblk) {
-      block(j, std::true_type{}, scA, scB, false);
-    }
-    mbar_wait_poll(bar_pvdone + 8 * ((nblk - 1) & 1), ((nblk - 1) >> 1) & 1);   // MMAs complete in order: all PVs are done
-    tc_fence_after();
-    const float inv = 1.f / l_run;
-    const int qi = q0 + i * 128 + row;
-    __half* optr = p.out + (static_cast<long long>(b) * p.nq + qi) * p.ldo + head * DH;
-#pragma unroll
-    for (int c0 = 0; c0 < DH; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_x32(orow + c0, r);
-      tmem_ld_wait();
-      if (qi < p.nq) {
-#pragma unroll
-        for (int u = 0; u < 32; u += 8) {
-          uint4 v;
-          v.x = pack_h2(__uint_as_float(r[u]) * inv, __uint_as_float(r[u + 1]) * inv);
-          v.y = pack_h2(__uint_as_float(r[u + 2]) * inv, __uint_as_float(r[u + 3]) * inv);
-          v.z = pack_h2(__uint_as_float(r[u + 4]) * inv, __uint_as_float(r[u + 5]) * inv);
-          v.w = pack_h2(__uint_as_float(r[u + 6]) * inv, __uint_as_float(r[u + 7]) * inv);
-          *reinterpret_cast<uint4*>(optr + c0 + u) = v;
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
 static long long* g_attn_dbg = nullptr;
 static bool nkv_blocks_for_stagger(int nkv) { return nkv > 4 * kKVTile; }   // pointless for a handful of key blocks
 
@@ -1273,31 +966,6 @@ static int launch_attention_v3(const mgld_attention_desc* d, cudaStream_t stream
     attr_set = true;
   }
   dim3 grid(ceil_div(d->nq, 256), d->heads, d->batch);
-  static int use_v5 = -1;   // MGLD_ATTN_V5: 64-key blocks, double-buffered S / P (attention_v5_kernel)
-  if (use_v5 < 0) { const char* e = getenv("MGLD_ATTN_V5"); use_v5 = e ? (atoi(e) != 0) : 0; }
-  if (use_v5 && !p.dbg) {
-    CUtensorMap tmK5, tmV5;
-    const int kvb = d->kv_batched ? d->batch : 1;
-    uint32_t box5[3] = {64, (uint32_t)kV5Keys, 1};
-    uint64_t dimsk[3] = {(uint64_t)d->ldk, (uint64_t)d->nkv, (uint64_t)kvb};
-    uint64_t strk[2] = {(uint64_t)d->ldk * 2, (uint64_t)d->ldk * 2 * d->nkv};
-    int rc = make_tmap_f16(&tmK5, d->k, 3, dimsk, strk, box5);
-    if (rc) return rc;
-    uint64_t dimsv[3] = {(uint64_t)d->ldv, (uint64_t)d->nkv, (uint64_t)kvb};
-    uint64_t strv[2] = {(uint64_t)d->ldv * 2, (uint64_t)d->ldv * 2 * d->nkv};
-    rc = make_tmap_f16(&tmV5, d->v, 3, dimsv, strv, box5);
-    if (rc) return rc;
-    const int smem5 = 2 * 16384 + kV5Stages * 2 * 8192 + 1024;
-    static const Fn kFns5[3] = {attention_v5_kernel<0>, attention_v5_kernel<2>, attention_v5_kernel<4>};
-    static bool attr5 = false;
-    if (!attr5) {
-      for (int i = 0; i < 3; ++i) MGLD_CUDA(cudaFuncSetAttribute(kFns5[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smem5));
-      attr5 = true;
-    }
-    MGLD_CUDA(launch_pdl(kFns5[attn_v3_emu() / 2], grid, dim3(kV3Threads), smem5, stream, tmQ, tmK5, tmV5, p));
-    MGLD_LAUNCH_CHECK("attention_v5_kernel");
-    return MGLD_OK;
-  }
   MGLD_CUDA(launch_pdl(kFns[p.dbg ? 3 : attn_v3_emu() / 2], grid, dim3(kV3Threads), smem, stream, tmQ, tmK, tmV, p));
   MGLD_LAUNCH_CHECK("attention_v3_kernel");
   return MGLD_OK;

@@ -47,9 +47,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         ms = bench(lambda: ops.attention(q, kv, kv, **kw))
         print(f"  cross B{B} N{N} h{heads} nkv77: max-rel {err:.2e}  {ms*1e3:8.1f} us", flush=True)
 else:
-    for name, env in (("v3 emu2", {"MGLD_ATTN_EMU": "2"}), ("v5 emu0", {"MGLD_ATTN_V5": "1", "MGLD_ATTN_EMU": "0"}),
-                      ("v5 emu2", {"MGLD_ATTN_V5": "1", "MGLD_ATTN_EMU": "2"}), ("v5 emu4", {"MGLD_ATTN_V5": "1", "MGLD_ATTN_EMU": "4"}),
-                      ("v3 emu2 again", {"MGLD_ATTN_EMU": "2"})):
+    for name, env in (("v2", {"MGLD_ATTN_V2": "1"}), ("v3 emu0", {"MGLD_ATTN_EMU": "0"}), ("v3 emu2", {"MGLD_ATTN_EMU": "2"}),
+                      ("v3 emu4", {"MGLD_ATTN_EMU": "4"})):
         print(f"== {name}", flush=True)
         e = dict(os.environ); e.update(env)
         subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=e, timeout=600)

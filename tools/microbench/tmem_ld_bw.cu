@@ -28,14 +28,14 @@ __global__ void __launch_bounds__(256, 1) k(int iters, unsigned long long* out, 
     if (kMode == 0) {
       tmem_ld_x32(base + (it & 3) * 32, r);
       tmem_ld_wait();
-      acc += r[it & 31];
+      acc += r[0] ^ r[13] ^ r[31];
     } else if (kMode == 1) {
       uint32_t a[32], b[32], c[32];
       tmem_ld_x32(base, r); tmem_ld_x32(base + 32, a); tmem_ld_x32(base + 64, b); tmem_ld_x32(base + 96, c);
       tmem_ld_wait();
-      acc += r[it & 31] + a[it & 31] + b[it & 31] + c[it & 31];
+      acc += (r[0] ^ a[7]) + (b[19] ^ c[31]) + (r[31] ^ a[0] ^ b[0] ^ c[0]);
     } else {
-      r[it & 31] += it;
+      r[0] += it; r[17] ^= it;
       tmem_st_x32(base + (it & 3) * 32, r);
       tmem_st_wait();
     }
