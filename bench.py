@@ -419,15 +419,19 @@ def main():
         return ms.item()
 
     clip_dev = clip_host.to(dev, non_blocking=True)
-    # warm-up: >= 3 passes.  Config 2/3: the whole clip.  Configs 4/5 (tens of seconds per pass): the first 2 segments of the
-    # clip — same unit shapes, so every CUDA graph / allocator pool the timed pass uses is warm.
-    warm_dev = clip_dev if args.config in (2, 3) else clip_dev[:min(n_frames, 2 * T)]
+    # warm-up: >= 3 passes.  Config 2/3: the whole clip.  Configs 4/5 (tens of seconds per pass): a prefix of the clip long
+    # enough that EVERY rank gets at least two units (units are sampled in pairs: the graphs of the paired batch shape must
+    # exist on every rank before the timed pass) — same unit shapes, so every CUDA graph / allocator pool is warm.
+    units_per_segment = {4: 2, 5: 6}.get(args.config, 1)
+    warm_segments = max(2, -(-2 * world // units_per_segment))
+    warm_dev = clip_dev if args.config in (2, 3) else clip_dev[:min(n_frames, warm_segments * T)]
     warm_flows = flows
     for _ in range(args.warmup):
         if warm_dev is clip_dev:
             sr = run_clip(clip_dev)
         else:
-            sr = pipe(warm_dev, context=context, flows_override=None if flows is None else flows[:2], world_size=world, rank=rank)
+            sr = pipe(warm_dev, context=context, flows_override=None if flows is None else flows[:warm_segments],
+                      world_size=world, rank=rank)
     assert torch.isfinite(sr).all(), "non-finite output"
 
     # ---- device-resident throughput ---------------------------------------------------------------------------------------

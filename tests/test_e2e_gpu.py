@@ -105,7 +105,14 @@ def test_pipeline_vs_reference_script_golden(name):
     assert sr.shape == (T, 3, Hh, Ww) and torch.isfinite(sr).all()
     units = [(x[k * T:(k + 1) * T], o[k * T:(k + 1) * T]) for x, o in caps for k in range(o.shape[0] // T)]
     assert len(units) == len(gold["units"])
-    for (x_T, samples), g in zip(units, gold["units"]):
+    # yardstick: the reference's deployment numerics (the oracle under fp16 autocast) on the same inputs and noise stream
+    ac_trace, rng = [], DeviceRng(42)
+    rng.seed()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        PR.sr_segment(sd, TINY_UNET, TINY_STRUCT, dd, vq_sd, dd, seg, ctx, rng, ddpm_steps=S, vqgantile_size=ts,
+                      vqgantile_stride=st, colorfix=cf, upsample_scale=us, trace=ac_trace)
+    assert len(ac_trace) == len(units)
+    for (x_T, samples), g, ac in zip(units, gold["units"], ac_trace):
         assert rel_err(x_T.cpu(), g["x_T"]) < 3e-3                      # LR latent (VAE encoder) + the shared noise stream
         # The golden run has 2 DDPM steps: its t=999 step turns eps into x0 with the factor sqrt(1/abar_999 - 1) = 14.6, so
         # the latents have a range of +-70..160 (random-init nets) and carry the fp16 eps error times 14.6, which the second
@@ -116,9 +123,14 @@ def test_pipeline_vs_reference_script_golden(name):
         # t=999 whose value moves by percents under ANY fp16-level change of its input (seen when only the batch composition
         # of the VAE encoder changed) -> the 99.9th percentile and the mean are asserted, the max only as a sanity bound.
         d = (samples.cpu() - g["samples"]).abs()
+        d_ac = (ac["samples"].float().cpu() - g["samples"]).abs()
         rng_ = g["samples"].abs().max()
-        assert torch.quantile(d.flatten(), 0.999) / rng_ < 1.5e-2, torch.quantile(d.flatten(), 0.999) / rng_
-        assert d.max() / rng_ < 0.15, d.max() / rng_
+        q, q_ac = torch.quantile(d.flatten(), 0.999) / rng_, torch.quantile(d_ac.flatten(), 0.999) / rng_
+        print(f"[golden {name}] latents vs reference run: 99.9th pct error / range {q:.2e} (fp16-autocast oracle {q_ac:.2e}), "
+              f"max {d.max() / rng_:.2e} ({d_ac.max() / rng_:.2e}), mean / std {d.mean() / g['samples'].std():.2e} "
+              f"({d_ac.mean() / g['samples'].std():.2e})")
+        assert q < max(1.5e-2, 2.0 * q_ac), (q, q_ac)         # no further from the reference run than 2x its own fp16 path
+        assert d.max() / rng_ < max(0.15, 2.0 * d_ac.max() / rng_), d.max() / rng_
         assert d.mean() / g["samples"].std() < 5e-3, d.mean() / g["samples"].std()
     ok, stats = robust_close(F.avg_pool2d(sr, 4).cpu(), gold["sr_pool4"].float(), 2e-3, 1e-2)
     assert ok, stats

@@ -12,7 +12,7 @@ echo "== bench (mgld arm)"; python bench.py --steps 5 --warmup 3 > $o/${tag}_ben
 echo "== bench (reference arm)"; python bench.py --impl reference --steps 2 --warmup 1 > $o/${tag}_bench_reference_arm.json 2> $o/${tag}_bench_reference_arm.err; head -c 300 $o/${tag}_bench_reference_arm.json; echo
 echo "== ncu launch list (one eager struct-encoder + UNet tile-step, T=10)"
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active
-MGLD_T=10 MGLD_PDL=0 timeout 1500 ncu --metrics $M --clock-control none -s 900 -c 900 --csv --log-file $o/${tag}_ncu_launches_tile_step_T10.csv python tools/ncu_target.py 2 > $o/${tag}_ncu_launches.log 2>&1
+MGLD_T=10 MGLD_PDL=0 timeout 1500 ncu --metrics $M --clock-control none --profile-from-start off --csv --log-file $o/${tag}_ncu_launches_tile_step_T10.csv python tools/ncu_target.py 2 > $o/${tag}_ncu_launches.log 2>&1
 wc -l $o/${tag}_ncu_launches_tile_step_T10.csv
 echo "== ncu --set full: attention (64x64 self-attention, B=5)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:attention_v3 -s 1 -c 1 -f -o $o/${tag}_prof_attention python tools/ncu_attn_target.py > $o/${tag}_ncu_attn.log 2>&1
