@@ -12,6 +12,8 @@ computed per frame as GEMM (fp32 scores) -> row softmax -> GEMM with V^T produce
 single channel-slotted buffer: each growth conv writes its 32 channels into its own 64-wide slot, so no torch.cat and
 no copy ever happens.
 """
+import os
+
 import torch
 
 from . import ops as _cuda_ops
@@ -68,11 +70,13 @@ class _AttnBlock:
         self.wv, self.bv = P.conv(p + ".v")
         self.wo, self.bo = P.conv(p + ".proj_out")
 
-    # bytes of fp32 scores per query panel.  The N x N score matrix of a frame never exists: queries are processed in panels
-    # of `rows` x N scores sized to stay resident in the 126 MB L2 between the three launches that touch them (QK^T GEMM ->
-    # row softmax -> PV GEMM), so HBM sees Q, K, V and O once instead of 829 MB of fp32 scores + 415 MB of fp16 P per frame
-    # at a 960x960 tile (N = 14400).
-    PANEL_BYTES = 32 << 20
+    # Bytes of fp32 scores per query panel.  Queries are processed in panels of `rows` x N scores so that the softmax and the
+    # PV GEMM read the scores / probabilities from the 126 MB L2 instead of HBM.  Measured on one frame of a 960x960 tile
+    # (N = 14400, ncu without cache flushing, profiles/r02_ncu_vae_attention_960*.csv): one panel per frame (the r01
+    # behaviour) moves 2.74 GB of reads + 1.42 GB of writes through DRAM; 32 MB panels 0.65 GB + 1.27 GB (the write-back L2
+    # still cleans every dirty score line to DRAM) — against 59 MB of Q + K + V + O.  64 MB keeps a 512x512 frame (N = 4096)
+    # in one panel.  A fused flash kernel (no scores in memory at all) is the open item: DESIGN.md §9.4.
+    PANEL_BYTES = int(os.environ.get("MGLD_VAE_PANEL_MB", "64")) << 20
 
     def __call__(self, ops, x):
         T, H, W, C = x.shape
