@@ -46,6 +46,7 @@ struct ConvGemmParams {
   int stages, tmem_cols, acc_stride;
   int panel_cols;  // fp16 output columns per staging panel: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B)
   int epilogue, act, has_res, out_f32;
+  int raster;    // 0: consecutive work units walk the M tiles of one N tile; 1: they walk the N tiles of one M tile
   int cta_pair;  // 1: launched as clusters of 2; one cta_group::2 MMA computes the two M tiles of a pair, each CTA stages half of B
   const float* bias;
   float alpha, beta;
@@ -132,7 +133,8 @@ __device__ __forceinline__ void store_stage32_f32(uint8_t* staging, int row, int
 // kPair instantiation must be launched as clusters of 2 (a kernel containing cta_group::2 instructions cannot be launched
 // without a cluster: cudaErrorInvalidClusterSize), hence two instantiations rather than a runtime flag.
 // kVariant: 0 = every epilogue option is a runtime flag; 1..4 = the common LINEAR epilogues with the flags folded at
-// compile time (1: +bias; 2: +bias, residual; 3: raw fp32 out (split-K partials); 4: +bias, SiLU).  With runtime flags the
+// compile time (1: +bias; 2: +bias, residual; 3: raw fp32 out (split-K partials); 4: +bias, SiLU; 5: GEGLU without
+// residual; 6: SPADE).  With runtime flags the
 // per-32-column step hops through six distant code islands (parameter load -> branch), paying instruction-fetch and
 // constant-load latency on every hop in a single-warp latency chain.
 template <bool kPair, int kVariant>
@@ -166,9 +168,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_k = p.taps * p.kchunks;
   const int total_units = tiles_mw * p.tiles_n * p.split_k;  // work units of a worker (CTA or CTA pair)
   constexpr bool kGen = kVariant == 0;
-  const int epi = kGen ? p.epilogue : MGLD_EPI_LINEAR;
+  constexpr int kEpiFixed = kVariant == 5 ? MGLD_EPI_GEGLU : kVariant == 6 ? MGLD_EPI_SPADE : MGLD_EPI_LINEAR;
+  const int epi = kGen ? p.epilogue : kEpiFixed;
   const int act = kGen ? p.act : (kVariant == 4 ? MGLD_ACT_SILU : MGLD_ACT_NONE);
-  const bool has_res = kGen ? (p.has_res != 0) : (kVariant == 2);
+  const bool has_res = kGen ? (p.has_res != 0) : (kVariant == 2 || (kVariant == 6 && p.has_res != 0));
   const bool out_f32 = kGen ? (p.out_f32 != 0) : (kVariant == 3);
   const bool unit_alpha = kGen ? (p.alpha == 1.f) : true;   // variants 1, 3, 4 require alpha == 1; 2 uses the residual form
   const bool pair_spade = epi == MGLD_EPI_SPADE;
@@ -210,8 +213,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // returns false for the padding M tile of an odd tile count (pair mode): its box lies beyond T, loads are zero-filled
   auto tile_coords = [&](int unit, int& x0, int& y0, int& t0, int& nt) -> bool {
     const int tile = unit / p.split_k;   // the splits of one tile run on neighbouring workers
-    const int tm = (tile % tiles_mw) * cs + static_cast<int>(rank);
-    nt = tile / tiles_mw;
+    int tmw;
+    if (p.raster) { tmw = tile / p.tiles_n; nt = tile - tmw * p.tiles_n; }
+    else { nt = tile / tiles_mw; tmw = tile - nt * tiles_mw; }
+    const int tm = tmw * cs + static_cast<int>(rank);
     x0 = (tm % p.tiles_w) * p.BW;
     y0 = ((tm / p.tiles_w) % p.tiles_h) * p.BH;
     t0 = (tm / (p.tiles_w * p.tiles_h)) * p.BT;
@@ -276,11 +281,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t rb = smem_u32(&res_full);
           const int c0 = nt * p.n_out_tile;
           const int np = has_res ? p.n_panels : 0;
-          mbar_expect_tx(rb, np * (p.panel_cols == 32 ? kPanelBytes / 2 : kPanelBytes) + (pair_spade ? kPanelBytes : 0));
+          mbar_expect_tx(rb, np * (p.panel_cols == 32 ? kPanelBytes / 2 : kPanelBytes) + (pair_spade ? p.n_panels * kPanelBytes : 0));
           const int pbytes = p.panel_cols == 32 ? kPanelBytes / 2 : kPanelBytes;
           for (int q = 0; q < np; ++q)
             tma_load_4d(smem_base + p.off_staging + q * pbytes, &tmRes, rb, c0 + q * p.panel_cols, x0, y0, t0);
-          if (pair_spade) tma_load_4d(smem_base + p.off_hstage, &tmH, rb, c0, x0, y0, t0);
+          if (pair_spade)
+            for (int q = 0; q < p.n_panels; ++q)
+              tma_load_4d(smem_base + p.off_hstage + q * kPanelBytes, &tmH, rb, c0 + q * 64, x0, y0, t0);
         }
       }
       if (p.dbg) { p.dbg[blockIdx.x * 16 + 0] = dbg_wait; p.dbg[blockIdx.x * 16 + 1] = clock64() - dbg_t0; }
@@ -401,7 +408,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // at the start of the NEXT tile's conversion (it has long finished by then) and the closing barrier disappears.
     const bool defer_drain = !(has_res || pair_spade);
     auto bias_of = [&](int unit) {   // this thread's bias element of work unit `unit` (block_n <= 256 = one per thread)
-      const int n = ((unit / p.split_k) / tiles_mw) * p.block_n + e;
+      const int tl = unit / p.split_k;
+      const int n = (p.raster ? tl % p.tiles_n : tl / tiles_mw) * p.block_n + e;
       return (p.bias && e < p.block_n && n < p.N) ? __ldg(p.bias + n) : 0.f;
     };
     if (worker < total_units) bias_s0[e] = bias_of(worker);
@@ -506,18 +514,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           else mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[buf]), 0));
         }
       } else {
-        // pair epilogues: ONE 64-column output panel; group g converts its 32-column half
+        // pair epilogues: 64-column output panels, each from 128 accumulator columns (value | gate, gamma | beta in blocks
+        // of 64).  block_n = 128: one panel, group g converts its 32-column half; block_n = 256: group g converts panel g.
+        const int npan = p.n_panels;
+        const int pn = npan == 2 ? grp : 0;
         if (grp < ngroups) {
-          for (int c0 = grp * 32; c0 < 64; c0 += ngroups * 32) {
+          for (int c0 = (npan == 2 ? 0 : grp * 32); c0 < 64; c0 += (npan == 2 ? 32 : ngroups * 32)) {
+            const int ac = pn * 128 + c0;   // accumulator column of the value / gamma slice; gate / beta at +64
+            const int oc = pn * 64 + c0;    // output column within the tile
             if (epi == MGLD_EPI_GEGLU) {
               float v[32], g[32];
-              tmem_ld_x32(trow + c0, reinterpret_cast<uint32_t*>(v));
-              tmem_ld_x32(trow + 64 + c0, reinterpret_cast<uint32_t*>(g));
+              tmem_ld_x32(trow + ac, reinterpret_cast<uint32_t*>(v));
+              tmem_ld_x32(trow + ac + 64, reinterpret_cast<uint32_t*>(g));
               tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {   // 16-byte shared loads of the two bias slices, packed adds
-                const float4 bv = *reinterpret_cast<const float4*>(bias_s + c0 + i);
-                const float4 bg = *reinterpret_cast<const float4*>(bias_s + 64 + c0 + i);
+                const float4 bv = *reinterpret_cast<const float4*>(bias_s + ac + i);
+                const float4 bg = *reinterpret_cast<const float4*>(bias_s + ac + 64 + i);
                 fadd2(v[i], v[i + 1], v[i], v[i + 1], bv.x, bv.y);
                 fadd2(v[i + 2], v[i + 3], v[i + 2], v[i + 3], bv.z, bv.w);
                 fadd2(g[i], g[i + 1], g[i], g[i + 1], bg.x, bg.y);
@@ -531,45 +544,49 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
               if (has_res) {
                 float r[32];
-                load_stage32(staging, row, c0, r, p.panel_cols);
+                load_stage32(staging, row, oc, r, 64);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = fmaf(p.alpha, v[i], p.beta * r[i]);
               }
-              store_stage32(staging, row, c0, v, 64);
+              store_stage32(staging, row, oc, v, 64);
             } else {  // SPADE: out = beta*res + GNaffine(h) * (1 + gamma) + beta_s
               const int tt = min(t0 + row / (p.BW * p.BH), p.T - 1);
-              const int cbase = nt * 64;
+              const int cbase = nt * p.n_out_tile + oc;
               float gm[32], bt[32], hv[32];
-              tmem_ld_x32(trow + c0, reinterpret_cast<uint32_t*>(gm));
-              tmem_ld_x32(trow + 64 + c0, reinterpret_cast<uint32_t*>(bt));
+              tmem_ld_x32(trow + ac, reinterpret_cast<uint32_t*>(gm));
+              tmem_ld_x32(trow + ac + 64, reinterpret_cast<uint32_t*>(bt));
               tmem_ld_wait();
-              load_stage32(hstage, row, c0, hv, 64);
+              load_stage32(hstage, row, oc, hv, 64);
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                const int c = cbase + c0 + i;
+                const int c = cbase + i;
                 const int g = c / p.ch_per_group;
                 const float2 st = __ldg(reinterpret_cast<const float2*>(p.gn_stats) + tt * p.groups + g);
                 const float xn = fmaf((hv[i] - st.x) * st.y, __ldg(p.gn_weight + c), __ldg(p.gn_bias + c));
-                gm[i] = fmaf(xn, 1.f + gm[i] + bias_s[c0 + i], bt[i] + bias_s[64 + c0 + i]);
+                gm[i] = fmaf(xn, 1.f + gm[i] + bias_s[ac + i], bt[i] + bias_s[ac + 64 + i]);
               }
               if (has_res) {
                 float r[32];
-                load_stage32(staging, row, c0, r, p.panel_cols);
+                load_stage32(staging, row, oc, r, 64);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) gm[i] = fmaf(p.beta, r[i], gm[i]);
               }
-              store_stage32(staging, row, c0, gm, 64);
+              store_stage32(staging, row, oc, gm, 64);
             }
           }
         }
         tc_fence_before();
         if (!pair || rank == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
         else mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[buf]), 0));
-        fence_proxy_async_smem();
-        named_bar_sync(1, 256);   // both halves of the panel are in smem
-        if (e == 0 && tile_valid) {
-          tma_store_4d(&tmOut, smem_base + p.off_staging, out_c0, x0, y0, t_store);
-          tma_store_commit();
+        if (npan == 2) {
+          store_panel(grp);       // each group stores the panel it converted
+        } else {
+          fence_proxy_async_smem();
+          named_bar_sync(1, 256);   // both halves of the panel are in smem
+          if (e == 0 && tile_valid) {
+            tma_store_4d(&tmOut, smem_base + p.off_staging, out_c0, x0, y0, t_store);
+            tma_store_commit();
+          }
         }
       }
       const long long tc1 = (p.dbg && e == 0) ? clock64() : 0;
@@ -806,12 +823,24 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
   }
   const int workers = p.cta_pair ? sms / 2 : sms;
   const int tiles_mw = p.cta_pair ? ceil_div(p.tiles_m, 2) : p.tiles_m;
-  p.block_n = pair ? 128 : (d->block_n > 0 ? d->block_n : pick_block_n(d->N, tiles_mw, workers));
+  // pair epilogues: 128 accumulator columns per 64-column output panel.  Two panels per tile (block_n = 256) halve the
+  // per-tile costs of the short-K FF1 / SPADE layers (tile bookkeeping, barriers, the producers' per-chunk issue time):
+  // -15 % on the FF1 GEMMs of the 64x64 .. 16x16 levels, +16 .. +40 % where the tiles no longer fill two waves
+  // (profiles/r02_conv_gemm_wide_pair_epilogue_raster.log) - so a wide tile is charged 1.7 narrow ones and the waves decide.
+  // MGLD_CONV_PAIR_EPI_BN=128|256 forces.
+  int pair_bn = 128;
+  if (pair && d->N % 256 == 0) {
+    const char* e = getenv("MGLD_CONV_PAIR_EPI_BN");
+    const int force = e ? atoi(e) : 0;
+    const int w128 = ceil_div(tiles_mw * (d->N / 128), workers), w256 = ceil_div(tiles_mw * (d->N / 256), workers);
+    if (force == 256 || (force == 0 && 17 * w256 < 10 * w128)) pair_bn = 256;
+  }
+  p.block_n = pair ? pair_bn : (d->block_n > 0 ? d->block_n : pick_block_n(d->N, tiles_mw, workers));
   if (d->out_f32 && p.block_n > 128) p.block_n = 128;  // fp32 staging tile: 128 x 128 x 4 B = 64 KB
   MGLD_CHECK_ARG(p.block_n % 32 == 0 && p.block_n >= 32 && p.block_n <= 256, "conv_gemm: block_n=%d", p.block_n);
   p.tiles_n = ceil_div(d->N, p.block_n);
   p.split_k = split_k; p.k_per_split = ceil_div(ntaps * p.kchunks, split_k); p.slab_frames = slab_frames;
-  p.n_out_tile = pair ? 64 : p.block_n;
+  p.n_out_tile = pair ? p.block_n / 2 : p.block_n;
   p.n_out_total = pair ? d->N / 2 : d->N;
   // columns beyond n_out_total are clipped by the TMA store; only the row pitch needs 16-byte alignment
   MGLD_CHECK_ARG(d->out_f32 ? d->ldout % 4 == 0 : d->ldout % 8 == 0, "conv_gemm: output row pitch %d not 16-byte aligned", d->ldout);
@@ -826,11 +855,23 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
   p.gn_stats = d->gn_stats; p.gn_weight = d->gn_weight; p.gn_bias = d->gn_bias;
   p.groups = d->groups; p.ch_per_group = d->groups > 0 ? p.n_out_total / d->groups : 1;
   p.dbg = g_dbg;
+  {
+    // Order of the work units.  N-major (consecutive units walk the M tiles of one weight tile) keeps the weight tile
+    // hot and is right for the 3x3 convolutions; M-major (consecutive units = the N tiles of one pixel tile, running
+    // concurrently on neighbouring SMs) reads the activations once and wins on the 1x1 GEMMs of the large levels (FF2 at
+    // 64x64: 105 MB of activations, 49.6 -> 40.0 us; the C x C projections -5..8 %) while the 3x3 convolutions of the
+    // 32x32 / 16x16 levels lose 6-11 % with it (profiles/r02_conv_gemm_wide_pair_epilogue_raster.log).
+    // MGLD_CONV_RASTER=0|1 forces.
+    const char* e = getenv("MGLD_CONV_RASTER");
+    const double a_bytes = 2.0 * d->T * d->H * d->W * (d->C1 + d->C2);
+    const bool m_major = p.tiles_n > 1 && (ntaps == 1 ? a_bytes >= 12e6 : a_bytes > 48e6);
+    p.raster = e ? (atoi(e) != 0 && p.tiles_n > 1) : m_major;
+  }
 
   // shared memory plan: [A/B ring][staging panels][h panel (SPADE)][bias]
   const int stage_bytes = kABytes + (p.block_n / (p.cta_pair ? 2 : 1)) * 128;
   const int staging_bytes = d->out_f32 ? p.n_panels * kPanelBytes : p.n_out_tile * kBlockM * 2;
-  const int hstage_bytes = d->epilogue == MGLD_EPI_SPADE ? kPanelBytes : 0;
+  const int hstage_bytes = d->epilogue == MGLD_EPI_SPADE ? p.n_panels * kPanelBytes : 0;
   const int fixed = staging_bytes + hstage_bytes + 2048 /*bias, two tiles*/ + 1024 /*alignment slack*/;
   int stages = (224 * 1024 - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -879,14 +920,14 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
   }
 
   using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvGemmParams);
-  static const KernelFn kKernels[2][5] = {
+  static const KernelFn kKernels[2][7] = {
       {conv_gemm_kernel<false, 0>, conv_gemm_kernel<false, 1>, conv_gemm_kernel<false, 2>, conv_gemm_kernel<false, 3>,
-       conv_gemm_kernel<false, 4>},
+       conv_gemm_kernel<false, 4>, conv_gemm_kernel<false, 5>, conv_gemm_kernel<false, 6>},
       {conv_gemm_kernel<true, 0>, conv_gemm_kernel<true, 1>, conv_gemm_kernel<true, 2>, conv_gemm_kernel<true, 3>,
-       conv_gemm_kernel<true, 4>}};
+       conv_gemm_kernel<true, 4>, conv_gemm_kernel<true, 5>, conv_gemm_kernel<true, 6>}};
   if (!g_attr_set) {
     for (int i = 0; i < 2; ++i)
-      for (int j = 0; j < 5; ++j)
+      for (int j = 0; j < 7; ++j)
         MGLD_CUDA(cudaFuncSetAttribute(kKernels[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     g_attr_set = true;
   }
@@ -898,6 +939,10 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
     else if (!d->res && d->out_f32 && d->alpha == 1.f) variant = 3;
   } else if (d->epilogue == MGLD_EPI_LINEAR && d->act == MGLD_ACT_SILU && !d->res && !d->out_f32 && d->alpha == 1.f) {
     variant = 4;
+  } else if (d->epilogue == MGLD_EPI_GEGLU && !d->res) {
+    variant = 5;
+  } else if (d->epilogue == MGLD_EPI_SPADE) {
+    variant = 6;
   }
   { const char* ev = getenv("MGLD_CONV_VARIANT"); if (ev && atoi(ev) == 0) variant = 0; }
   const KernelFn kernel = kKernels[p.cta_pair ? 1 : 0][variant];

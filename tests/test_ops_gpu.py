@@ -130,6 +130,40 @@ def test_temporal_conv(T, H, W, C):
     assert rel_err(O.conv_gemm(x, w, **kw), E.conv_gemm(x, w, **kw)) < 4e-3
 
 
+@pytest.mark.parametrize("cta_pair", ["0", "1"])
+def test_pair_epilogue_tile_widths_and_unit_order(monkeypatch, cta_pair):
+    """GEGLU / SPADE with one (block_n 128) and two (block_n 256) output panels per tile, N-major and M-major order of the
+    work units, single CTAs and CTA pairs: the same accumulation order per output element, so the same bits."""
+    O = ops()
+    monkeypatch.setenv("MGLD_CONV_PAIR", cta_pair)
+    T, H, W = 3, 20, 28                      # ragged pixel tiles
+    a = rnd(T, H, W, 320).half()
+    w, b = rnd(1536, 320, scale=320 ** -0.5).half(), rnd(1536)
+    wp, bp = O.interleave_pair(w[:768], w[768:]), O.interleave_pair(b[:768], b[768:])
+    y = a.float() @ w.float().t() + b
+    ref_g = y[..., :768] * F.gelu(y[..., 768:])
+    Ch, C = 128, 256
+    actv, h, res = rnd(T, H, W, Ch).half(), rnd(T, H, W, C).half(), rnd(T, H, W, C).half()
+    wg, wb = O.pack_conv_weight(rnd(C, Ch, 3, 3, scale=0.03)), O.pack_conv_weight(rnd(C, Ch, 3, 3, scale=0.03, seed=5))
+    st = O.gn_finalize(O.gn_stats(h), H * W, C, 1e-5)
+    kw = dict(taps=9, bias=O.interleave_pair(rnd(C, scale=0.1), rnd(C, scale=0.1, seed=3)), epilogue=O.EPI_SPADE, h=h, gn_stats=st,
+              gn_weight=rnd(C, seed=7), gn_bias=rnd(C, seed=9), groups=32, res=res, beta=1.0)
+    ws = O.interleave_pair(wg, wb)
+    ref_s = E.conv_gemm(actv, ws, **kw)
+    outs = []
+    for bn in ("128", "256"):
+        for raster in ("0", "1"):
+            monkeypatch.setenv("MGLD_CONV_PAIR_EPI_BN", bn)
+            monkeypatch.setenv("MGLD_CONV_RASTER", raster)
+            g = O.conv_gemm(a, wp, bias=bp, epilogue=O.EPI_GEGLU)
+            sp = O.conv_gemm(actv, ws, **kw)
+            lin = O.conv_gemm(a, w, bias=b, res=None)
+            assert rel_err(g, ref_g) < 4e-3 and rel_err(sp, ref_s) < 4e-3 and rel_err(lin, y) < 4e-3, (bn, raster)
+            outs.append((g, sp, lin))
+    for o in outs[1:]:
+        assert all(torch.equal(x, y0) for x, y0 in zip(o, outs[0]))
+
+
 def test_geglu_and_spade_epilogues():
     O = ops()
     a = rnd(4096, 320).half()

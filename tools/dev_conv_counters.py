@@ -11,6 +11,8 @@ shapes = [(5, 64, 64, 320, 320, 9, 0), (5, 64, 64, 320, 320, 1, 0), (5, 64, 64, 
           (5, 64, 64, 320, 2560, 1, 128), (5, 64, 64, 1280, 320, 1, 0), (5, 32, 32, 640, 640, 1, 0), (5, 32, 32, 640, 5120, 1, 0),
           (5, 16, 16, 1280, 1280, 1, 0), (5, 256, 256, 256, 256, 9, 0)]
 if os.environ.get("MGLD_T") == "10": shapes = shapes_t10
+if os.environ.get("MGLD_KIND") == "geglu":      # FF1 layers: N = 2 x Cout interleaved, GEGLU epilogue
+    shapes = [(10, 64, 64, 320, 2560, 1, 0), (10, 32, 32, 640, 5120, 1, 0), (10, 16, 16, 1280, 10240, 1, 0)]
 so = L.lib()
 so.mgld_conv_gemm_set_debug_counters.argtypes = [ctypes.c_void_p]
 so.mgld_conv_gemm_set_debug_counters.restype = None
@@ -20,10 +22,13 @@ for pair in (sys.argv[1:] or ["0"]):
         x = torch.randn(T, H, W, Ci, device=dev).half(); w = (torch.randn(Co, taps * Ci, device=dev) * 0.02).half()
         b = torch.randn(Co, device=dev)
         out = torch.empty(T, H, W, Co, device=dev, dtype=torch.float16)
-        for _ in range(2): ops.conv_gemm(x, w, taps=taps, bias=b, out=out, block_n=bn)
+        kw = {}
+        if os.environ.get("MGLD_KIND") == "geglu":
+            kw = dict(epilogue=ops.EPI_GEGLU); out = torch.empty(T, H, W, Co // 2, device=dev, dtype=torch.float16)
+        for _ in range(2): ops.conv_gemm(x, w, taps=taps, bias=b, out=out, block_n=bn, **kw)
         dbg = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
         so.mgld_conv_gemm_set_debug_counters(ctypes.c_void_p(dbg.data_ptr()))
-        ops.conv_gemm(x, w, taps=taps, bias=b, out=out, block_n=bn)
+        ops.conv_gemm(x, w, taps=taps, bias=b, out=out, block_n=bn, **kw)
         torch.cuda.synchronize()
         so.mgld_conv_gemm_set_debug_counters(ctypes.c_void_p(0))
         d = dbg.view(148, 16).double()
