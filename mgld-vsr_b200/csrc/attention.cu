@@ -905,6 +905,10 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 
 
+// attention_kv80.cu: cross-attention against <= 80 shared keys (the 77 text tokens) on warp-level MMAs
+bool attention_kv80_supported(const mgld_attention_desc* d);
+int launch_attention_kv80(const mgld_attention_desc* d, cudaStream_t stream);
+
 static long long* g_attn_dbg = nullptr;
 static bool nkv_blocks_for_stagger(int nkv) { return nkv > 4 * kKVTile; }   // pointless for a handful of key blocks
 
@@ -989,6 +993,7 @@ extern "C" int mgld_attention(const mgld_attention_desc* d, void* stream) {
   MGLD_CHECK_ARG(d->ldq % 8 == 0 && d->ldk % 8 == 0 && d->ldv % 8 == 0 && d->ldo % 8 == 0,
                  "attention: row pitches must be multiples of 8 elements");
   MGLD_CHECK_ARG(d->q_col0 % 8 == 0 && d->k_col0 % 8 == 0 && d->v_col0 % 8 == 0, "attention: column offsets");
+  if (attention_kv80_supported(d)) return launch_attention_kv80(d, (cudaStream_t)stream);   // short shared context
   if (d->head_dim == 64) {
     // v2 (two query tiles per CTA, P in TMEM) pays off once there are >= 256 queries; MGLD_ATTN_V1=1 forces v1
     static const bool force_v1 = getenv("MGLD_ATTN_V1") != nullptr;

@@ -12,7 +12,8 @@ def bench(fn, n=20):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-for (B, N, heads, dh) in [(5, 4096, 5, 64), (5, 4096, 4, 64), (5, 1024, 10, 64), (5, 256, 20, 64), (5, 1024, 4, 64)]:
+B0 = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+for (B, N, heads, dh) in [(B0, 4096, 5, 64), (B0, 4096, 4, 64), (B0, 1024, 10, 64), (B0, 256, 20, 64), (B0, 1024, 4, 64)]:
     C = heads * dh
     qkv = torch.randn(B * N, 3 * C, device=dev).half()
     out = torch.empty(B * N, C, device=dev, dtype=torch.float16)
