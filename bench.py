@@ -328,6 +328,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--ddpm-steps", type=int, default=50)
     ap.add_argument("--frames", type=int, default=0, help="override the clip length (development)")
+    ap.add_argument("--clips-per-batch", type=int, default=0, help="units sampled in lock-step as one (b t) batch (default: the pipeline's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the second (host-buffer) timed pass (long single-GPU runs of configs 4/5)")
@@ -380,6 +381,9 @@ def main():
     context = torch.randn(1, 77, 1024, generator=g).to(dev)
     model.cond_stage_model.set_embedding(context)
     pipe = VSRPipeline(model, vq, ddpm_steps=args.ddpm_steps, seed=42)
+    if args.clips_per_batch > 0:
+        pipe.clips_per_batch = args.clips_per_batch
+        model.unet_clips_per_call = max(model.unet_clips_per_call, args.clips_per_batch)
     T = cfg.model.params.num_frames
     n_seg = (n_frames + T - 1) // T
     lr_h, lr_w = C["lr"]
@@ -419,19 +423,24 @@ def main():
         return ms.item()
 
     clip_dev = clip_host.to(dev, non_blocking=True)
-    # warm-up: >= 3 passes.  Config 2/3: the whole clip.  Configs 4/5 (tens of seconds per pass): a prefix of the clip long
-    # enough that EVERY rank gets at least two units (units are sampled in pairs: the graphs of the paired batch shape must
-    # exist on every rank before the timed pass) — same unit shapes, so every CUDA graph / allocator pool is warm.
+    # warm-up: >= 3 passes.  Config 2/3: the whole clip.  Configs 4/5 (tens of seconds per pass): a prefix of the clip with
+    # the same unit shapes, long enough that EVERY rank gets a full group of units.  Units are sampled in groups of
+    # clips_per_batch plus one smaller remainder group (pipeline._sr_units), each group size a different (b t) batch shape
+    # with its own CUDA graphs; which sizes a rank meets depends on its unit count, so the warm-up passes cycle through
+    # the group sizes (clips_per_batch .. 1) and every graph the timed pass can need exists on every rank before it.
     units_per_segment = {4: 2, 5: 6}.get(args.config, 1)
-    warm_segments = max(2, -(-2 * world // units_per_segment))
+    warm_segments = min(n_seg, max(2, -(-pipe.clips_per_batch * world // units_per_segment)))
     warm_dev = clip_dev if args.config in (2, 3) else clip_dev[:min(n_frames, warm_segments * T)]
-    warm_flows = flows
-    for _ in range(args.warmup):
+    sizes = list(range(max(1, pipe.clips_per_batch), 0, -1))
+    cpb = pipe.clips_per_batch
+    for i in range(max(args.warmup, len(sizes)) if warm_dev is not clip_dev else args.warmup):
         if warm_dev is clip_dev:
             sr = run_clip(clip_dev)
         else:
+            pipe.clips_per_batch = sizes[i % len(sizes)]
             sr = pipe(warm_dev, context=context, flows_override=None if flows is None else flows[:warm_segments],
                       world_size=world, rank=rank)
+    pipe.clips_per_batch = cpb
     assert torch.isfinite(sr).all(), "non-finite output"
 
     # ---- device-resident throughput ---------------------------------------------------------------------------------------

@@ -344,7 +344,7 @@ class LatentDiffusionVSRTextWT(_ModuleBase):
         self._steps = _StepRunner(self)
         # one graph replay per DDPM step (tiles + posterior + guidance); False / MGLD_WHOLE_STEP=0: eps-only graph + eager tail
         self.whole_step_graph = os.environ.get("MGLD_WHOLE_STEP", "1") != "0"
-        self.unet_clips_per_call = 2      # clips (num_frames each) batched through one struct-encoder + UNet evaluation
+        self.unet_clips_per_call = 4      # clips (num_frames each) batched through one struct-encoder + UNet evaluation
         # struct encoder of step i-1 as a concurrent graph branch of step i (_EpsRunner._pipelined).  Correct (tests) but
         # measured neutral on a power-capped B200 (DDPM loop 772 -> 769 ms, profiles/r01_dev_run42*): off by default.
         self.pipeline_struct_encoder = False

@@ -111,7 +111,7 @@ def wavelet_reconstruction(content_feat, style_feat, levels=5):
 class VSRPipeline:
     def __init__(self, model, vq_model, ddpm_steps=50, n_frames=5, upscale=4.0, vqgantile_size=960,
                  vqgantile_stride=750, tile_overlap=32, colorfix_type="adain", seed=42, dec_w=1.0, guidance_scale=-10.0,
-                 clips_per_batch=2, input_size=512):
+                 clips_per_batch=4, input_size=512):
         self.model, self.vq = model, vq_model
         self.S, self.n_frames, self.upscale = ddpm_steps, n_frames, upscale
         self.tile, self.stride, self.tile_overlap = vqgantile_size, vqgantile_stride, tile_overlap
@@ -119,6 +119,7 @@ class VSRPipeline:
         self.keep_latents = False                  # True: `last_latents` holds the sampled latents of every unit (see save_latents_npy)
         self.last_latents = None
         self.clips_per_batch = clips_per_batch     # independent units (segments / VAE tiles) sampled in lock-step
+        self.vae_clips_per_pass = 2                # units per VAE encode / decode pass (bounds the full-resolution activations)
         self.latent_tile = int(input_size / 8)     # script :450 tile_size=int(opt.input_size/8), --input_size 512
         if getattr(vq_model, "decoder", None) is not None:
             vq_model.decoder.fusion_w = dec_w                                     # script :306
@@ -185,6 +186,9 @@ class VSRPipeline:
         per-frame), then per unit exactly the script's sequence — re-seed, posterior sample, x_T noise."""
         m, T = self.model, ims[0].shape[0]
         from .autoencoder import DiagonalGaussianDistribution
+        if len(ims) > self.vae_clips_per_pass:
+            P = self.vae_clips_per_pass
+            return [u for k in range(0, len(ims), P) for u in self._prepare_units(ims[k:k + P])]
         post = m.encode_first_stage(ims[0] if len(ims) == 1 else torch.cat(ims, 0))
         out = []
         for k in range(len(ims)):
@@ -211,6 +215,9 @@ class VSRPipeline:
         nf = self.vq.dd.get("num_frames") if hasattr(self.vq, "dd") else None
         if K > 1 and nf != T:                      # the temporal layers can only split whole clips of num_frames
             return [self._finish_units(samples[k * T:(k + 1) * T], [ims[k]])[0] for k in range(K)]
+        if K > self.vae_clips_per_pass:
+            P = self.vae_clips_per_pass
+            return [x for k in range(0, K, P) for x in self._finish_units(samples[k * T:(k + P) * T], ims[k:k + P])]
         im = ims[0] if K == 1 else torch.cat(ims, 0)
         _, enc_fea = self.vq.encode(im)
         x = self.vq.decode(samples * (1.0 / self.model.scale_factor), enc_fea)
