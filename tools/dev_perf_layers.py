@@ -36,6 +36,7 @@ LAYERS = [  # (kind, H, C_in, N_out, taps)
     ("lin", 64, 320, 320, 1), ("lin", 64, 320, 960, 1), ("lin", 32, 640, 1920, 1),
     ("res", 64, 1280, 320, 1), ("res", 32, 2560, 640, 1), ("res", 16, 5120, 1280, 1),
     ("lin", 64, 320, 320, 9), ("lin", 64, 960, 320, 9), ("lin", 32, 640, 640, 9), ("lin", 16, 1280, 1280, 9),
+    ("lin", 16, 2560, 1280, 9), ("lin", 8, 1280, 1280, 9), ("lin", 8, 2560, 1280, 9), ("res", 8, 1280, 1280, 1), ("res", 8, 5120, 1280, 1),
 ]
 tot = 0.0
 for kind, H, Ci, No, taps in LAYERS:
