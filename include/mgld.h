@@ -112,7 +112,7 @@ typedef struct mgld_attention_desc {
   int32_t ldq, ldk, ldv;
   int32_t q_col0, k_col0, v_col0;
   int32_t q_head_stride, k_head_stride, v_head_stride;
-  int32_t batch, heads, head_dim; /* head_dim 64 or 128 */
+  int32_t batch, heads, head_dim; /* head_dim 64, 128 or 512 (512: the VAE middle attention, model.py:247-305) */
   int32_t nq, nkv;
   int32_t kv_batched;
   float scale;

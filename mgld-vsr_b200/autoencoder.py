@@ -6,9 +6,10 @@
                            VideoDecoder_Mix = SD decoder + SpatialTemporalConv after every ResnetBlock + two
                            encoder-feature fusion blocks; ldm/modules/diffusionmodules/model.py:473-572, 926-1056)
 
-All convolutions run through the tcgen05 implicit-GEMM kernel; the single-head head-dim-512 middle attention is
-computed per frame as GEMM (fp32 scores) -> row softmax -> GEMM with V^T produced directly by an operand-swapped GEMM
-(the V bias is added after P V, exact because softmax rows sum to one).  The ResidualDenseBlock concat chain is a
+All convolutions run through the tcgen05 implicit-GEMM kernel; the single-head head-dim-512 middle attention is one
+fused q|k|v projection GEMM + the split-D flash kernel of csrc/attention_hd512.cu (head widths without a fused kernel
+fall back to GEMM (fp32 scores) -> row softmax -> GEMM per L2-sized query panel, with V^T produced directly by an
+operand-swapped GEMM and the V bias added after P V, exact because softmax rows sum to one).  The ResidualDenseBlock concat chain is a
 single channel-slotted buffer: each growth conv writes its 32 channels into its own 64-wide slot, so no torch.cat and
 no copy ever happens.
 """
@@ -65,9 +66,14 @@ class _AttnBlock:
 
     def __init__(self, P, p):
         self.norm = P.norm(p + ".norm")
-        self.wq, self.bq = P.conv(p + ".q")
-        self.wk, self.bk = P.conv(p + ".k")
-        self.wv, self.bv = P.conv(p + ".v")
+        wq, bq = P.conv(p + ".q")
+        wk, bk = P.conv(p + ".k")
+        wv, bv = P.conv(p + ".v")
+        C = wq.shape[0]
+        # one [3C, C] weight: the fused path projects q | k | v with ONE GEMM; the panelled path uses its row blocks
+        self.wqkv, self.bqkv = torch.cat([wq, wk, wv], 0).contiguous(), torch.cat([bq, bk, bv], 0).contiguous()
+        self.wq, self.wk, self.wv = self.wqkv[:C], self.wqkv[C:2 * C], self.wqkv[2 * C:]
+        self.bq, self.bk, self.bv = self.bqkv[:C], self.bqkv[C:2 * C], self.bqkv[2 * C:]
         self.wo, self.bo = P.conv(p + ".proj_out")
 
     # Bytes of fp32 scores per query panel.  Queries are processed in panels of `rows` x N scores so that the softmax and the
@@ -75,13 +81,22 @@ class _AttnBlock:
     # (N = 14400, ncu without cache flushing, profiles/r02_ncu_vae_attention_960*.csv): one panel per frame (the r01
     # behaviour) moves 2.74 GB of reads + 1.42 GB of writes through DRAM; 32 MB panels 0.65 GB + 1.27 GB (the write-back L2
     # still cleans every dirty score line to DRAM) — against 59 MB of Q + K + V + O.  64 MB keeps a 512x512 frame (N = 4096)
-    # in one panel.  A fused flash kernel (no scores in memory at all) is the open item: DESIGN.md §9.4.
+    # in one panel.  Only head widths without a fused kernel (see FUSED_HEAD_DIMS) still take this path.
     PANEL_BYTES = int(os.environ.get("MGLD_VAE_PANEL_MB", "64")) << 20
+    # head widths with a fused attention kernel; MGLD_VAE_FUSED_ATTN=0 forces the panelled GEMM -> softmax -> GEMM path
+    FUSED_HEAD_DIMS = (64, 128, 512) if os.environ.get("MGLD_VAE_FUSED_ATTN", "1") != "0" else ()
 
     def __call__(self, ops, x):
         T, H, W, C = x.shape
         N = H * W
         xn = _gn_silu(ops, x, self.norm, 1e-6, silu=False).reshape(T * N, C)
+        if C in self.FUSED_HEAD_DIMS:
+            # flash kernel (C = 512: csrc/attention_hd512.cu): no score matrix in memory
+            qkv = ops.conv_gemm(xn, self.wqkv, bias=self.bqkv)
+            o = ops.attention(qkv, qkv, qkv, batch=T, heads=1, head_dim=C, nq=N, nkv=N, scale=float(C) ** -0.5,
+                              q_col0=0, k_col0=C, v_col0=2 * C)
+            out = ops.conv_gemm(o, self.wo, bias=self.bo, res=x.reshape(T * N, C), beta=1.0)
+            return out.reshape(T, H, W, C)
         q = ops.conv_gemm(xn, self.wq, bias=self.bq)
         k = ops.conv_gemm(xn, self.wk, bias=self.bk)
         o = torch.empty(T * N, C, device=x.device, dtype=torch.float16)

@@ -908,6 +908,8 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 // attention_kv80.cu: cross-attention against <= 80 shared keys (the 77 text tokens) on warp-level MMAs
 bool attention_kv80_supported(const mgld_attention_desc* d);
 int launch_attention_kv80(const mgld_attention_desc* d, cudaStream_t stream);
+// attention_hd512.cu: head dim 512 (the VAEs' single-head middle attention), split-D flash kernel
+int launch_attention_hd512(const mgld_attention_desc* d, cudaStream_t stream);
 
 static long long* g_attn_dbg = nullptr;
 static bool nkv_blocks_for_stagger(int nkv) { return nkv > 4 * kKVTile; }   // pointless for a handful of key blocks
@@ -988,11 +990,12 @@ extern "C" int mgld_attention(const mgld_attention_desc* d, void* stream) {
   if (!initialised()) { set_error("mgld_init() has not been called"); return MGLD_ERR_NOT_INIT; }
   MGLD_CHECK_ARG(d && d->q && d->k && d->v && d->out, "attention: null pointer");
   MGLD_CHECK_ARG(d->nq > 0 && d->nkv > 0 && d->heads > 0 && d->batch > 0, "attention: bad sizes");
-  MGLD_CHECK_ARG(d->head_dim == 64 || d->head_dim == 128, "attention: head_dim %d not supported (64, 128)",
-                 d->head_dim);
+  MGLD_CHECK_ARG(d->head_dim == 64 || d->head_dim == 128 || d->head_dim == 512,
+                 "attention: head_dim %d not supported (64, 128, 512)", d->head_dim);
   MGLD_CHECK_ARG(d->ldq % 8 == 0 && d->ldk % 8 == 0 && d->ldv % 8 == 0 && d->ldo % 8 == 0,
                  "attention: row pitches must be multiples of 8 elements");
   MGLD_CHECK_ARG(d->q_col0 % 8 == 0 && d->k_col0 % 8 == 0 && d->v_col0 % 8 == 0, "attention: column offsets");
+  if (d->head_dim == 512) return launch_attention_hd512(d, (cudaStream_t)stream);
   if (attention_kv80_supported(d)) return launch_attention_kv80(d, (cudaStream_t)stream);   // short shared context
   if (d->head_dim == 64) {
     // v2 (two query tiles per CTA, P in TMEM) pays off once there are >= 256 queries; MGLD_ATTN_V1=1 forces v1

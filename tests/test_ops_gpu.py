@@ -245,6 +245,34 @@ def test_attention_no_max_fast_path_fallback(case, B, N, heads):
     assert rel_err(got, ref) < 4e-3, rel_err(got, ref)
 
 
+@pytest.mark.parametrize("group", ["4", "2"])
+@pytest.mark.parametrize("B,N,gain", [(1, 64, 1.0), (2, 200, 1.0), (2, 4096, 1.0), (1, 14400, 1.0), (1, 1000, 6.0), (1, 1024, -1.0)])
+def test_attention_head_dim_512(monkeypatch, group, B, N, gain):
+    """the VAEs' single-head middle attention (model.py:247-305) on the split-D flash kernel (attention_hd512.cu): one
+    key block, ragged tails of the 128-row query tile and the 64-key block, a 512^2 frame (N = 4096), a 960^2 VAE tile
+    (N = 14400), peaky logits, and scores that keep rising with the key index (every block moves the lazy maximum: the
+    O rescale path); with 4 and 2 slabs per TMA operation."""
+    if group != "4" and N > 4096:
+        pytest.skip("the large case runs once")
+    monkeypatch.setenv("MGLD_HD512_GROUP", group)
+    O = ops()
+    C = 512
+    qkv = rnd(B * N, 3 * C, seed=5).reshape(B, N, 3, C)
+    if gain > 0:
+        qkv[:, :, 1] *= gain
+    else:
+        qkv[:, :, 1] *= torch.linspace(0.2, 8.0, N, device=DEV).reshape(1, N, 1)
+    qkv = qkv.reshape(B * N, 3 * C).half()
+    kw = dict(batch=B, heads=1, head_dim=C, nq=N, nkv=N, scale=C ** -0.5, q_col0=0, k_col0=C, v_col0=2 * C)
+    got = O.attention(qkv, qkv, qkv, **kw)
+    ref = _sdpa_ref(qkv, B, N, 1, C)
+    assert torch.isfinite(got).all()
+    err = rel_err(got, ref)
+    print(f"[hd512 group={group} B={B} N={N} gain={gain}] rel err {err:.2e}; per 64-col slab: "
+          + " ".join(f"{rel_err(got[:, c:c + 64], ref[:, c:c + 64]):.1e}" for c in range(0, C, 64)))
+    assert err < 4e-3, err
+
+
 def test_attention_cross_77_keys_full_shape():
     """the 77-key cross-attention variant at the shapes the UNet runs it (15 of the 34 attention launches of a
     tile-step): N=4096 x 5 heads, 1024 x 10, 256 x 20, K/V broadcast over the frames, peaky logits included"""

@@ -1,5 +1,6 @@
 """Profiling target: the VAE mid attention block (single head, d=512) on one frame of a 960x960 VAE tile (N = 120*120 = 14400
-tokens), L2-resident query panels (autoencoder._AttnBlock).  Run under
+tokens): fused path (q|k|v GEMM + split-D flash kernel, csrc/attention_hd512.cu) by default, the panelled GEMM ->
+softmax -> GEMM path with MGLD_VAE_FUSED_ATTN=0 (autoencoder._AttnBlock).  Run under
   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --profile-from-start off --csv ...
 Algorithmic traffic of the attention proper: Q + K + V + O = 4 * 14400 * 512 * 2 B = 59 MB (the N x N scores in fp32 + P in
 fp16 would be 829 + 415 MB written and read again)."""
