@@ -657,28 +657,13 @@ __global__ void splitk_finalize_kernel(const SplitFinalizeParams p) {
     float a[8], b[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) { a[u] = 0.f; b[u] = 0.f; }
-    // the slabs are summed in slab order (deterministic); the loads of up to four slabs are issued before the first add, so
-    // a thread keeps 128-256 bytes in flight instead of one slab's 32-64
-    for (int s0 = 0; s0 < p.S; s0 += 4) {
-      float4 x0[4], x1[4], y0[4], y1[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (s0 + u < p.S) {
-          const float* row = p.ws + (s0 + u) * p.slab_stride + m * p.ldws;
-          x0[u] = *reinterpret_cast<const float4*>(row + ca); x1[u] = *reinterpret_cast<const float4*>(row + ca + 4);
-          if (pair) { y0[u] = *reinterpret_cast<const float4*>(row + ca + 64); y1[u] = *reinterpret_cast<const float4*>(row + ca + 68); }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (s0 + u < p.S) {
-          a[0] += x0[u].x; a[1] += x0[u].y; a[2] += x0[u].z; a[3] += x0[u].w;
-          a[4] += x1[u].x; a[5] += x1[u].y; a[6] += x1[u].z; a[7] += x1[u].w;
-          if (pair) {
-            b[0] += y0[u].x; b[1] += y0[u].y; b[2] += y0[u].z; b[3] += y0[u].w;
-            b[4] += y1[u].x; b[5] += y1[u].y; b[6] += y1[u].z; b[7] += y1[u].w;
-          }
-        }
+    for (int s = 0; s < p.S; ++s) {
+      const float* row = p.ws + s * p.slab_stride + m * p.ldws;
+      const float4 x0 = *reinterpret_cast<const float4*>(row + ca), x1 = *reinterpret_cast<const float4*>(row + ca + 4);
+      a[0] += x0.x; a[1] += x0.y; a[2] += x0.z; a[3] += x0.w; a[4] += x1.x; a[5] += x1.y; a[6] += x1.z; a[7] += x1.w;
+      if (pair) {
+        const float4 y0 = *reinterpret_cast<const float4*>(row + ca + 64), y1 = *reinterpret_cast<const float4*>(row + ca + 68);
+        b[0] += y0.x; b[1] += y0.y; b[2] += y0.z; b[3] += y0.w; b[4] += y1.x; b[5] += y1.y; b[6] += y1.z; b[7] += y1.w;
       }
     }
     float r[8];

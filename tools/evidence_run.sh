@@ -16,6 +16,10 @@ MGLD_T=10 MGLD_PDL=0 timeout 1500 ncu --metrics $M --clock-control none --profil
 wc -l $o/${tag}_ncu_launches_tile_step_T10.csv
 echo "== ncu --set full: attention (64x64 self-attention, B=5)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:attention_v3 -s 1 -c 1 -f -o $o/${tag}_prof_attention python tools/ncu_attn_target.py > $o/${tag}_ncu_attn.log 2>&1
+echo "== ncu --set full: cross-attention against the 77 text tokens (warp-level MMA kernel)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:cross_attention_kv80 -s 1 -c 1 -f -o $o/${tag}_prof_attention_kv80 python tools/ncu_attn_target.py > $o/${tag}_ncu_attn_kv80.log 2>&1
+echo "== ncu --set full: head-dim-512 flash attention of the VAE middle block (one frame of a 960x960 tile)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_hd512 -c 1 -f -o $o/${tag}_prof_attention_hd512 python tools/ncu_vae_attn_target.py > $o/${tag}_ncu_attn_hd512.log 2>&1
 echo "== ncu --set full: conv_gemm (six representative launches)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_gemm -c 6 -f -o $o/${tag}_prof_conv_gemm python tools/ncu_conv_target.py > $o/${tag}_ncu_conv.log 2>&1
 ls -la $o | grep ${tag}_prof
