@@ -578,7 +578,8 @@ def measure_rooflines(model, ops, dev, context, T):
     a_ms = sum(e0.elapsed_time(e1) for e0, e1, *_ in rec_a)
     a_fl = sum(r[2] for r in rec_a)
     big = [r for r in rec_a if r[3] >= 4096 and r[4] >= 4096]
-    attn = {"kernel": "mgld::attention_v3_kernel (tcgen05 flash attention, d=64)", "bound": "tensor",
+    attn = {"kernel": "all mgld_attention launches of the tile-step: mgld::attention_v3_kernel (tcgen05 flash attention, d=64), "
+                      "cross_attention_kv80_kernel (77 text tokens), attention_kernel (small maps / d=128)", "bound": "tensor",
             "achieved": a_fl / (a_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": a_fl / (a_ms * 1e-3) / 1e12 / peak,
             "traffic": None, "peak_source": src, "launches_timed": len(rec_a), "flop_per_tile_step_in_kernel": a_fl,
             "ms_per_tile_step_in_kernel": a_ms, "frames_per_tile_step": T}

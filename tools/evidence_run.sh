@@ -10,10 +10,12 @@ echo "== pytest -m gpu"; python -m pytest tests -m gpu -q -s > $o/${tag}_gpu_tes
 echo "== smoke"; python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee $o/${tag}_smoke.log
 echo "== bench (mgld arm)"; python bench.py --steps 5 --warmup 3 > $o/${tag}_bench.json 2> $o/${tag}_bench.err; head -c 400 $o/${tag}_bench.json; echo
 echo "== bench (reference arm)"; python bench.py --impl reference --steps 2 --warmup 1 > $o/${tag}_bench_reference_arm.json 2> $o/${tag}_bench_reference_arm.err; head -c 300 $o/${tag}_bench_reference_arm.json; echo
+if [ "${SKIP_LIST:-0}" != "1" ]; then
 echo "== ncu launch list (one eager struct-encoder + UNet tile-step, T=10)"
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active
 MGLD_T=10 MGLD_PDL=0 timeout 1500 ncu --metrics $M --clock-control none --profile-from-start off --csv --log-file $o/${tag}_ncu_launches_tile_step_T10.csv python tools/ncu_target.py 2 > $o/${tag}_ncu_launches.log 2>&1
 wc -l $o/${tag}_ncu_launches_tile_step_T10.csv
+fi
 echo "== ncu --set full: attention (64x64 self-attention, B=5)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:attention_v3 -s 1 -c 1 -f -o $o/${tag}_prof_attention python tools/ncu_attn_target.py > $o/${tag}_ncu_attn.log 2>&1
 echo "== ncu --set full: cross-attention against the 77 text tokens (warp-level MMA kernel)"
