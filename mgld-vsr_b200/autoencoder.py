@@ -50,6 +50,8 @@ class _ResnetBlock:
     def __call__(self, ops, x, x2=None, out=None, pool=None):
         a1 = _gn_silu(ops, x, self.n1, 1e-6, True, x2)
         s1 = pool.next() if pool is not None else None
+        if s1 is None:
+            s1 = ops.conv_stats_slot(a1.shape[0], a1.shape[1] * a1.shape[2], a1.device)   # sums of h from conv1's epilogue
         h = _tag(ops.conv_gemm(a1, self.w1, taps=TAPS_3X3, bias=self.b1, stats_out=s1), s1)
         a2 = _gn_silu(ops, h, self.n2, 1e-6, True)
         if self.skip is not None:

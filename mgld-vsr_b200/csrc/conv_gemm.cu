@@ -54,7 +54,9 @@ struct ConvGemmParams {
   const float* gn_weight;
   const float* gn_bias;
   int groups, ch_per_group;
-  uint32_t off_staging, off_hstage, off_bias;  // byte offsets from the 1024-aligned smem base
+  uint32_t off_staging, off_hstage, off_bias, off_stats;  // byte offsets from the 1024-aligned smem base
+  double* stats_out;           // variant 7: [T, stats_groups, 2] x 16-byte fixed-point (sum, sumsq) accumulators of the output
+  int stats_groups, stats_cpg; // groups of the consumer's GroupNorm, channels per group
   long long* dbg;  // optional per-CTA cycle counters [grid][16] (mgld_conv_gemm_set_debug_counters); null in production
 };
 
@@ -130,11 +132,23 @@ __device__ __forceinline__ void store_stage32_f32(uint8_t* staging, int row, int
 }
 
 
+// Variant 7 (GroupNorm statistics of the output accumulated by the epilogue): (sum, sumsq) accumulators in shared memory,
+// two buffers (tile parity) of kStatsGroups groups x 2 moments x {integer part, 2^-40 fraction} (fixsum, common.h)
+constexpr int kStatsGroups = 66;   // block_n <= 256 columns / >= 4 channels per group, + 1 for a tile that starts mid-group
+constexpr int kStatsBytes = 2 * kStatsGroups * 2 * 16;
+__device__ __forceinline__ void fixsum_add_words(unsigned long long* w, float v) {
+  const float fl = floorf(v);
+  atomicAdd(w, (unsigned long long)__float2ll_rd(v));
+  atomicAdd(w + 1, (unsigned long long)__double2ll_rd((double)(v - fl) * 1099511627776.0));
+}
+
 // kPair instantiation must be launched as clusters of 2 (a kernel containing cta_group::2 instructions cannot be launched
 // without a cluster: cudaErrorInvalidClusterSize), hence two instantiations rather than a runtime flag.
 // kVariant: 0 = every epilogue option is a runtime flag; 1..4 = the common LINEAR epilogues with the flags folded at
 // compile time (1: +bias; 2: +bias, residual; 3: raw fp32 out (split-K partials); 4: +bias, SiLU; 5: GEGLU without
-// residual; 6: SPADE).  With runtime flags the
+// residual; 6: SPADE; 7: +bias and the GroupNorm statistics of the output for its consumer, long-K convolutions only: each
+// finished staging panel is summed column-wise by the epilogue group that converted it - the long mainloop hides the
+// extra work, the epilogue of a short-K GEMM would not, profiles/r01_dev_run7*).  With runtime flags the
 // per-32-column step hops through six distant code islands (parameter load -> branch), paying instruction-fetch and
 // constant-load latency on every hop in a single-warp latency chain.
 template <bool kPair, int kVariant>
@@ -173,7 +187,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int act = kGen ? p.act : (kVariant == 4 ? MGLD_ACT_SILU : MGLD_ACT_NONE);
   const bool has_res = kGen ? (p.has_res != 0) : (kVariant == 2 || (kVariant == 6 && p.has_res != 0));
   const bool out_f32 = kGen ? (p.out_f32 != 0) : (kVariant == 3);
-  const bool unit_alpha = kGen ? (p.alpha == 1.f) : true;   // variants 1, 3, 4 require alpha == 1; 2 uses the residual form
+  const bool unit_alpha = kGen ? (p.alpha == 1.f) : true;   // variants 1, 3, 4, 7 require alpha == 1; 2 uses the residual form
+  constexpr bool kStats = kVariant == 7;
   const bool pair_spade = epi == MGLD_EPI_SPADE;
 
   if (threadIdx.x == 0) {
@@ -399,6 +414,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* hstage = smem_gen + p.off_hstage;
     float* bias_s0 = reinterpret_cast<float*>(smem_gen + p.off_bias);   // two buffers of 256 floats (tile parity)
     constexpr int ngroups = 2;
+    unsigned long long* sacc = reinterpret_cast<unsigned long long*>(smem_gen + p.off_stats);   // variant 7 only
+    int prev_t = 0, prev_g0 = 0;
+    if constexpr (kStats) {
+      for (int i = e; i < kStatsBytes / 8; i += 256) sacc[i] = 0ull;   // ordered before any use by the first tile's opening barrier
+    }
+    // add the finished sums of buffer `b` (frame t, groups g0 ...) to the global accumulators and clear the buffer
+    auto flush_stats = [&](int b, int t, int g0) {
+      for (int i = e; i < kStatsGroups * 2; i += 256) {   // i = local group * 2 + moment
+        unsigned long long* w = sacc + (b * kStatsGroups * 2 + i) * 2;
+        const unsigned long long hi = w[0], lo = w[1];
+        if (hi | lo) {
+          unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.stats_out) +
+                                    ((static_cast<long long>(t) * p.stats_groups + g0 + (i >> 1)) * 2 + (i & 1)) * 2;
+          atomicAdd(dst, hi);
+          atomicAdd(dst + 1, lo);
+          w[0] = 0ull; w[1] = 0ull;
+        }
+      }
+    };
     const int cols_per_panel = out_f32 ? 32 : p.panel_cols;
     const int pbytes = (!out_f32 && p.panel_cols == 32) ? kPanelBytes / 2 : kPanelBytes;
     int lt = 0;
@@ -433,6 +467,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (p.dbg && e == 0) dbg_es += clock64() - td;
       }
       named_bar_sync(1, 256);
+      if constexpr (kStats) {
+        if (lt > 0) flush_stats((lt - 1) & 1, prev_t, prev_g0);   // every thread is past the previous tile's panel sums
+      }
       const long long tc0 = (p.dbg && e == 0) ? clock64() : 0;
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * p.acc_stride;
       // panel `pn` of this group is complete in smem -> its leader stores it
@@ -442,6 +479,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (leader && tile_valid && out_c0 + pn * cols_per_panel < p.n_out_total) {
           tma_store_4d(&tmOut, smem_base + p.off_staging + pn * pbytes, out_c0 + pn * cols_per_panel, x0, y0, t_store);
           tma_store_commit();
+        }
+      };
+
+      // variant 7: column sums of panel `pn` (complete in shared memory: store_panel() synchronised its group).  Thread ->
+      // one column and cols_per_panel of the 128 rows; a warp reads 32 consecutive columns of one row (conflict-free under
+      // either swizzle).  The values are the fp16-rounded outputs, i.e. what a gn_stats pass over the stored tensor reads.
+      auto panel_stats = [&](int pn) {
+        const int cpp = cols_per_panel;
+        const int cc = row & (cpp - 1), rp = row / cpp;
+        const int col = pn * cpp + cc;                       // column within the tile
+        const int c32 = col & ~31, chunk = (col & 31) >> 3, sub = (col & 7) * 2;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 4
+        for (int r = rp * cpp; r < (rp + 1) * cpp; r += 2) {
+          const float f0 = __half2float(*reinterpret_cast<const __half*>(stage_ptr16(staging, r, c32, chunk, p.panel_cols) + sub));
+          const float f1 = __half2float(*reinterpret_cast<const __half*>(stage_ptr16(staging, r + 1, c32, chunk, p.panel_cols) + sub));
+          s0 += f0; q0 = fmaf(f0, f0, q0);
+          s1 += f1; q1 = fmaf(f1, f1, q1);
+        }
+        if (tile_valid && out_c0 + col < p.n_out_total) {
+          const int g = (out_c0 + col) / p.stats_cpg - out_c0 / p.stats_cpg;
+          unsigned long long* w = sacc + (((lt & 1) * kStatsGroups + g) * 2) * 2;
+          fixsum_add_words(w, s0 + s1);
+          fixsum_add_words(w + 2, q0 + q1);
         }
       };
 
@@ -494,6 +555,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               else mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[buf]), 0));   // the pair's MMA issuer lives in the leader
             }
             store_panel(c0 / cols_per_panel);
+            if constexpr (kStats) panel_stats(c0 / cols_per_panel);
           }
         };
         float va[32], vb[32];
@@ -590,6 +652,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       const long long tc1 = (p.dbg && e == 0) ? clock64() : 0;
+      if constexpr (kStats) { prev_t = t0; prev_g0 = out_c0 / p.stats_cpg; }
       bias_s0[((lt + 1) & 1) * 256 + e] = bias_next;   // read after the next tile's opening barrier
       if (p.dbg && e == 0) dbg_ec += tc1 - tc0;
       if (!defer_drain) {
@@ -600,6 +663,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         named_bar_sync(1, 256);
       }
+    }
+    if constexpr (kStats) {
+      named_bar_sync(1, 256);
+      if (lt > 0) flush_stats((lt - 1) & 1, prev_t, prev_g0);
     }
     if (leader) tma_store_wait_all();
     if (p.dbg && e == 0) { p.dbg[blockIdx.x * 16 + 5] = dbg_we; p.dbg[blockIdx.x * 16 + 6] = clock64() - dbg_t0e; p.dbg[blockIdx.x * 16 + 7] = lt; p.dbg[blockIdx.x * 16 + 10] = dbg_ec; p.dbg[blockIdx.x * 16 + 11] = dbg_es; }
@@ -769,7 +836,10 @@ static int pair_mode_env() {
 
 using namespace mgld;
 
-static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int split_k, int slab_frames) {
+// `fused_stats` (optional): in = the caller wants d->stats_out accumulated by the epilogue if this launch qualifies;
+// out = whether it was (otherwise the caller runs the streaming gn_stats pass over the output)
+static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int split_k, int slab_frames,
+                            bool* fused_stats = nullptr) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!initialised()) { set_error("mgld_init() has not been called"); return MGLD_ERR_NOT_INIT; }
   MGLD_CHECK_ARG(d && d->a && d->w && d->out, "conv_gemm: null pointer");
@@ -868,11 +938,27 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
     p.raster = e ? (atoi(e) != 0 && p.tiles_n > 1) : m_major;
   }
 
-  // shared memory plan: [A/B ring][staging panels][h panel (SPADE)][bias]
+  // GroupNorm statistics of the output in the epilogue (variant 7): plain +bias epilogue, fp16 out, a long mainloop to hide
+  // the column sums behind (>= 18 K chunks: the 3x3 convolutions), tiles that lie inside one frame and inside the map
+  // (every row of a tile is a real pixel), whole groups of >= 4 channels.  MGLD_CONV_FUSED_STATS=0 switches it off.
+  bool fuse = false;
+  if (fused_stats && *fused_stats) {
+    static const int min_k = [] { const char* e = getenv("MGLD_CONV_FUSED_STATS_MIN_K"); return e ? atoi(e) : 18; }();
+    const char* ev = getenv("MGLD_CONV_VARIANT");
+    const int cpg = d->stats_groups > 0 ? d->N / d->stats_groups : 0;
+    fuse = d->epilogue == MGLD_EPI_LINEAR && d->act == MGLD_ACT_NONE && !d->res && !d->out_f32 && d->alpha == 1.f &&
+           split_k == 1 && p.BT == 1 && d->W % p.BW == 0 && d->H % p.BH == 0 && ntaps * p.kchunks >= min_k &&
+           d->stats_groups > 0 && d->N % d->stats_groups == 0 && cpg >= 4 && !(ev && atoi(ev) == 0);
+    p.stats_out = d->stats_out; p.stats_groups = d->stats_groups; p.stats_cpg = cpg > 0 ? cpg : 1;
+    *fused_stats = fuse;
+  }
+
+  // shared memory plan: [A/B ring][staging panels][h panel (SPADE)][bias][statistics (variant 7)]
   const int stage_bytes = kABytes + (p.block_n / (p.cta_pair ? 2 : 1)) * 128;
   const int staging_bytes = d->out_f32 ? p.n_panels * kPanelBytes : p.n_out_tile * kBlockM * 2;
   const int hstage_bytes = d->epilogue == MGLD_EPI_SPADE ? p.n_panels * kPanelBytes : 0;
-  const int fixed = staging_bytes + hstage_bytes + 2048 /*bias, two tiles*/ + 1024 /*alignment slack*/;
+  const int stats_bytes = fuse ? kStatsBytes : 0;
+  const int fixed = staging_bytes + hstage_bytes + 2048 /*bias, two tiles*/ + stats_bytes + 1024 /*alignment slack*/;
   int stages = (224 * 1024 - fixed) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   MGLD_CHECK_ARG(stages >= 2, "conv_gemm: tile does not fit in shared memory (block_n=%d)", p.block_n);
@@ -880,7 +966,8 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
   p.off_staging = stages * stage_bytes;
   p.off_hstage = p.off_staging + staging_bytes;
   p.off_bias = p.off_hstage + hstage_bytes;
-  const int smem = p.off_bias + 2048 + 1024;
+  p.off_stats = p.off_bias + 2048;
+  const int smem = p.off_stats + stats_bytes + 1024;
 
   // tensor maps
   const int lda = d->lda > 0 ? d->lda : d->C1;
@@ -920,14 +1007,14 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
   }
 
   using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvGemmParams);
-  static const KernelFn kKernels[2][7] = {
+  static const KernelFn kKernels[2][8] = {
       {conv_gemm_kernel<false, 0>, conv_gemm_kernel<false, 1>, conv_gemm_kernel<false, 2>, conv_gemm_kernel<false, 3>,
-       conv_gemm_kernel<false, 4>, conv_gemm_kernel<false, 5>, conv_gemm_kernel<false, 6>},
+       conv_gemm_kernel<false, 4>, conv_gemm_kernel<false, 5>, conv_gemm_kernel<false, 6>, conv_gemm_kernel<false, 7>},
       {conv_gemm_kernel<true, 0>, conv_gemm_kernel<true, 1>, conv_gemm_kernel<true, 2>, conv_gemm_kernel<true, 3>,
-       conv_gemm_kernel<true, 4>, conv_gemm_kernel<true, 5>, conv_gemm_kernel<true, 6>}};
+       conv_gemm_kernel<true, 4>, conv_gemm_kernel<true, 5>, conv_gemm_kernel<true, 6>, conv_gemm_kernel<true, 7>}};
   if (!g_attr_set) {
     for (int i = 0; i < 2; ++i)
-      for (int j = 0; j < 7; ++j)
+      for (int j = 0; j < 8; ++j)
         MGLD_CUDA(cudaFuncSetAttribute(kKernels[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     g_attr_set = true;
   }
@@ -945,6 +1032,7 @@ static int conv_gemm_single(const mgld_conv_gemm_desc* d, void* stream_, int spl
     variant = 6;
   }
   { const char* ev = getenv("MGLD_CONV_VARIANT"); if (ev && atoi(ev) == 0) variant = 0; }
+  if (fuse) variant = 7;
   const KernelFn kernel = kKernels[p.cta_pair ? 1 : 0][variant];
   const int total_units = tiles_mw * p.tiles_n * p.split_k;
   if (!p.cta_pair) {
@@ -1005,27 +1093,33 @@ extern "C" long long mgld_conv_gemm_workspace_bytes(const mgld_conv_gemm_desc* d
   return (long long)bytes;
 }
 
-static int conv_gemm_dispatch(const mgld_conv_gemm_desc* d, void* stream_);
+static int conv_gemm_dispatch(const mgld_conv_gemm_desc* d, void* stream_, bool* fused_stats);
 
 extern "C" int mgld_conv_gemm(const mgld_conv_gemm_desc* d, void* stream_) {
   if (!initialised()) { set_error("mgld_init() has not been called"); return MGLD_ERR_NOT_INIT; }
   MGLD_CHECK_ARG(d && d->a && d->w && d->out, "conv_gemm: null pointer");
-  int rc = conv_gemm_dispatch(d, stream_);
-  if (rc || !d->stats_out) return rc;
-  // GroupNorm statistics of the output for its consumer: a streaming pass over the (L2-resident) output.  Accumulating them
-  // in the conv epilogue (shuffles + shared/global atomics per tile) was measured slower than this pass (profiles/
-  // r01_dev_run7_fused_stats_regression.log), so the epilogue stays lean.
-  MGLD_CHECK_ARG(!d->out_f32 && d->stats_groups > 0, "conv_gemm: stats_out needs fp16 output and stats_groups > 0");
+  if (d->stats_out) MGLD_CHECK_ARG(!d->out_f32 && d->stats_groups > 0, "conv_gemm: stats_out needs fp16 output and stats_groups > 0");
+  bool fused = false;
+  int rc = conv_gemm_dispatch(d, stream_, &fused);
+  if (rc || !d->stats_out || fused) return rc;
+  // GroupNorm statistics of the output for its consumer: a streaming pass over the (L2-resident) output.  Only the long-K
+  // convolutions accumulate them in their epilogue (variant 7): for short-K GEMMs the epilogue is the critical path and the
+  // extra work was measured slower than this pass (profiles/r01_dev_run7_fused_stats_regression.log).
   const int n_out = d->epilogue == MGLD_EPI_LINEAR ? d->N : d->N / 2;
   return mgld_gn_stats_f16(reinterpret_cast<const __half*>(d->out) + d->out_col0, n_out, d->ldout, nullptr, 0, 0, d->T,
                            d->H * d->W, d->stats_groups, d->stats_out, stream_);
 }
 
-static int conv_gemm_dispatch(const mgld_conv_gemm_desc* d, void* stream_) {
+static int conv_gemm_dispatch(const mgld_conv_gemm_desc* d, void* stream_, bool* fused_stats) {
   int S, bn, ldws, sf;
   size_t bytes;
-  if (!d->workspace || !split_plan(d, &S, &bn, &bytes, &ldws, &sf) || (size_t)d->workspace_bytes < bytes)
-    return conv_gemm_single(d, stream_, 1, 0);
+  if (!d->workspace || !split_plan(d, &S, &bn, &bytes, &ldws, &sf) || (size_t)d->workspace_bytes < bytes) {
+    const char* ef = getenv("MGLD_CONV_FUSED_STATS");   // read per call (the tests toggle it)
+    const bool fuse_on = ef ? atoi(ef) != 0 : false;
+    *fused_stats = fuse_on && d->stats_out != nullptr;
+    return conv_gemm_single(d, stream_, 1, 0, fused_stats);
+  }
+  *fused_stats = false;
   // pass 1: raw partial sums.  The descriptor is rewritten to a plain fp32-output GEMM into the workspace.
   mgld_conv_gemm_desc r = *d;
   r.epilogue = MGLD_EPI_LINEAR; r.act = MGLD_ACT_NONE; r.bias = nullptr; r.alpha = 1.f; r.beta = 0.f; r.res = nullptr;

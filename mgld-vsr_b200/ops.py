@@ -327,6 +327,19 @@ _POOL_ALWAYS_ZERO = os.environ.get("MGLD_POOL_ALWAYS_ZERO", "0") != "0"   # deve
 _sums_pool = _SumsPool()
 
 
+# The long-K convolutions (3x3, >= 18 K chunks) can accumulate the GroupNorm sums of their output in their epilogue
+# (conv_gemm.cu variant 7) - one streaming pass and one launch less per normalisation of a > 16x16 map.
+FUSED_CONV_STATS = os.environ.get("MGLD_CONV_FUSED_STATS", "0") != "0"
+
+
+def conv_stats_slot(T, HW, device, groups=32):
+    """A zeroed accumulator slot to pass as `stats_out` of a 3x3 conv whose consumer is a GroupNorm over a map larger than
+    16x16 (smaller maps normalise in one launch, mgld_group_norm_f16), or None when the fused statistics are off."""
+    if not FUSED_CONV_STATS or HW <= 256:
+        return None
+    return _sums_pool.get(T, groups, device)
+
+
 def stats_pool_reset():
     """call at the start of a model forward (inside any CUDA-graph capture of it)"""
     _sums_pool.reset()

@@ -137,7 +137,10 @@ class _ResBlock:
     def __call__(self, ops, x, emb_bias, seg=None, x2=None, pool=None, actv=None):
         """seg: the struct-cond map of this resolution; actv: ReLU(mlp_shared(seg)) if the owner already computed it"""
         a1 = _gn_silu(ops, x, self.n1, 1e-5, True, x2)
+        T, HW = a1.shape[0], a1.shape[1] * a1.shape[2]
         s1 = pool.next() if pool is not None else None
+        if s1 is None:
+            s1 = ops.conv_stats_slot(T, HW, a1.device)      # statistics of h from the conv's own epilogue (long-K)
         h = _tag(ops.conv_gemm(a1, self.w1, taps=TAPS_3X3, bias=emb_bias[self.emb_idx], stats_out=s1), s1)
         a2 = _gn_silu(ops, h, self.n2, 1e-5, True)
         if self.skip is not None:
@@ -149,6 +152,8 @@ class _ResBlock:
         if not self.dual:
             return _tag(ops.conv_gemm(a2, self.w2, taps=TAPS_3X3, bias=self.b2, res=sk, beta=1.0, stats_out=so), so)
         s2 = pool.next() if pool is not None else None
+        if s2 is None:
+            s2 = ops.conv_stats_slot(T, HW, a2.device)
         h2 = ops.conv_gemm(a2, self.w2, taps=TAPS_3X3, bias=self.b2, stats_out=s2)
         T, H, W, C = h2.shape
         st = ops.gn_finalize(s2, H * W, C, 1e-5) if s2 is not None else \

@@ -116,6 +116,15 @@ def _cat(x1, x2):
     return x1 if x2 is None else torch.cat([x1, x2], dim=-1)
 
 
+FUSED_CONV_STATS = False
+
+
+def conv_stats_slot(T, HW, device, groups=32):
+    if not FUSED_CONV_STATS or HW <= 256:
+        return None
+    return torch.zeros(T, groups, 2, dtype=torch.float64)
+
+
 def stats_pool_reset():
     pass
 

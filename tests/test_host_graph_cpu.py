@@ -14,7 +14,11 @@ from oracle import torch_ref as R
 T = 2
 
 
-def test_unet_and_struct_encoder_host_graph():
+@pytest.mark.parametrize("fused_stats", [False, True])
+def test_unet_and_struct_encoder_host_graph(monkeypatch, fused_stats):
+    # fused_stats: the 3x3 convs of the > 16x16 levels hand the GroupNorm sums of their output to the consumer
+    # (ops.conv_stats_slot -> conv_gemm stats_out -> gn_apply / gn_finalize) instead of a group_norm call
+    monkeypatch.setattr(emu_ops, "FUSED_CONV_STATS", fused_stats)
     from mgld_vsr_b200.unet import InflatedEncoderUNetModelWT, InflatedUNetModelDualcondV2
     unet = InflatedUNetModelDualcondV2(**TINY_UNET, ops=emu_ops)
     se = InflatedEncoderUNetModelWT(**TINY_STRUCT, ops=emu_ops)
@@ -36,7 +40,9 @@ def test_unet_and_struct_encoder_host_graph():
         InflatedUNetModelDualcondV2(**TINY_UNET, ops=emu_ops).load_state_dict(bad, device="cpu")
 
 
-def test_vae_host_graph():
+@pytest.mark.parametrize("fused_stats", [False, True])
+def test_vae_host_graph(monkeypatch, fused_stats):
+    monkeypatch.setattr(emu_ops, "FUSED_CONV_STATS", fused_stats)
     from mgld_vsr_b200.autoencoder import AutoencoderKL, VideoAutoencoderKLResi
     gold = torch.load(os.path.join(GOLDEN, "tiny_vae.pt"))
     vq = VideoAutoencoderKLResi(ddconfig=TINY_DD, lossconfig={"target": "ldm.modules.losses.LPIPSWithDiscriminator"},

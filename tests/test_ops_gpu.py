@@ -120,6 +120,40 @@ def test_fused_groupnorm_statistics(T, H, W, Ci, Co, taps, res):
     assert torch.equal(sums.view(torch.int64), ref.view(torch.int64))    # order-independent accumulation: same bits
 
 
+@pytest.mark.parametrize("cta_pair", ["0", "1"])
+@pytest.mark.parametrize("T,H,W,Ci,Co,groups", [(5, 64, 64, 320, 320, 32), (10, 64, 64, 320, 320, 32), (2, 32, 32, 640, 640, 32),
+                                               (5, 64, 64, 256, 256, 32), (2, 128, 128, 128, 128, 32), (2, 64, 64, 960, 320, 32),
+                                               (3, 30, 46, 128, 256, 32), (5, 16, 16, 1280, 1280, 32), (1, 64, 64, 320, 320, 8)])
+def test_conv_epilogue_groupnorm_statistics(monkeypatch, cta_pair, T, H, W, Ci, Co, groups):
+    """MGLD_CONV_FUSED_STATS=1: a long-K 3x3 conv accumulates the (sum, sumsq) of its output for the consumer's GroupNorm in
+    its epilogue (conv_gemm.cu variant 7: column sums of every finished staging panel) instead of a streaming pass over the
+    stored output.  Same values up to the fp32 rounding of the per-thread partial sums; the output itself is bit-identical.
+    Shapes that do not qualify (partial tiles, split-K) fall back to the streaming pass inside the same call."""
+    O = ops()
+    x = rnd(T, H, W, Ci).half()
+    w = (rnd(Co, 9 * Ci, scale=(9 * Ci) ** -0.5)).half()
+    b = rnd(Co)
+    monkeypatch.setenv("MGLD_CONV_PAIR", cta_pair)
+    monkeypatch.setenv("MGLD_CONV_FUSED_STATS", "0")
+    ref_out = O.conv_gemm(x, w, taps=9, bias=b)
+    ref = O.gn_stats(ref_out.reshape(T, -1, Co), groups=groups)
+    for rep in range(2):                                                  # twice: bitwise repeatable
+        monkeypatch.setenv("MGLD_CONV_FUSED_STATS", "1")
+        sums = torch.zeros(T, groups, 2, 2, device=DEV, dtype=torch.float64)
+        out = O.conv_gemm(x, w, taps=9, bias=b, stats_out=sums, stats_groups=groups)
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref_out)
+        got, want = O.decode_sums(sums), O.decode_sums(ref)
+        assert torch.allclose(got, want, rtol=2e-5, atol=1e-3), (got - want).abs().max()
+        if rep == 0:
+            first = sums.clone()
+            print(f"[fused stats pair={cta_pair} {T}x{H}x{W} {Ci}->{Co}] same bits as the streaming pass: "
+                  f"{torch.equal(sums.view(torch.int64), ref.view(torch.int64))}, max rel diff "
+                  f"{((got - want).abs() / want.abs().clamp_min(1.0)).max():.1e}")
+        else:
+            assert torch.equal(sums.view(torch.int64), first.view(torch.int64))
+
+
 @pytest.mark.parametrize("T,H,W,C", [(5, 8, 8, 1280), (5, 32, 32, 256), (2, 12, 20, 128)])
 def test_temporal_conv(T, H, W, C):
     O = ops()
