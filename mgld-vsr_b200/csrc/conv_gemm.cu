@@ -135,7 +135,8 @@ __device__ __forceinline__ void store_stage32_f32(uint8_t* staging, int row, int
 // Variant 7 (GroupNorm statistics of the output accumulated by the epilogue): (sum, sumsq) accumulators in shared memory,
 // two buffers (tile parity) of kStatsGroups groups x 2 moments x {integer part, 2^-40 fraction} (fixsum, common.h)
 constexpr int kStatsGroups = 66;   // block_n <= 256 columns / >= 4 channels per group, + 1 for a tile that starts mid-group
-constexpr int kStatsBytes = 2 * kStatsGroups * 2 * 16;
+constexpr int kStatsAccBytes = 2 * kStatsGroups * 2 * 16;
+constexpr int kStatsBytes = kStatsAccBytes + 2 * 128 * 8;   // + per epilogue group: 128 per-thread (sum, sumsq) partials
 __device__ __forceinline__ void fixsum_add_words(unsigned long long* w, float v) {
   const float fl = floorf(v);
   atomicAdd(w, (unsigned long long)__float2ll_rd(v));
@@ -417,7 +418,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     unsigned long long* sacc = reinterpret_cast<unsigned long long*>(smem_gen + p.off_stats);   // variant 7 only
     int prev_t = 0, prev_g0 = 0;
     if constexpr (kStats) {
-      for (int i = e; i < kStatsBytes / 8; i += 256) sacc[i] = 0ull;   // ordered before any use by the first tile's opening barrier
+      for (int i = e; i < kStatsAccBytes / 8; i += 256) sacc[i] = 0ull;   // ordered before any use by the first tile's opening barrier
     }
     // add the finished sums of buffer `b` (frame t, groups g0 ...) to the global accumulators and clear the buffer
     auto flush_stats = [&](int b, int t, int g0) {
@@ -498,11 +499,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           s0 += f0; q0 = fmaf(f0, f0, q0);
           s1 += f1; q1 = fmaf(f1, f1, q1);
         }
-        if (tile_valid && out_c0 + col < p.n_out_total) {
-          const int g = (out_c0 + col) / p.stats_cpg - out_c0 / p.stats_cpg;
-          unsigned long long* w = sacc + (((lt & 1) * kStatsGroups + g) * 2) * 2;
-          fixsum_add_words(w, s0 + s1);
-          fixsum_add_words(w + 2, q0 + q1);
+        // per-thread partials -> table -> one thread per (group, moment) sums its columns in a fixed order.  (Adding the
+        // partials straight into the shared accumulators was 40 threads per address: the epilogue took 1.5x the mainloop.)
+        float2* tab = reinterpret_cast<float2*>(sacc + kStatsAccBytes / 8) + grp * 128;
+        tab[row] = make_float2(s0 + s1, q0 + q1);            // index = rp * cpp + cc
+        named_bar_sync(2 + grp, 128);   // the next write of `tab` comes after the next panel's store_panel() barrier
+        const int cpg = p.stats_cpg;
+        const int ch0 = out_c0 + pn * cpp;                   // first channel of the panel
+        const int g_first = ch0 / cpg;
+        const int gl = row >> 1, mo = row & 1;
+        const int lo = max((g_first + gl) * cpg, ch0), hi = min(min((g_first + gl + 1) * cpg, ch0 + cpp), p.n_out_total);
+        if (tile_valid && lo < hi) {
+          float acc = 0.f;
+          const float* tf = reinterpret_cast<const float*>(tab) + mo;
+          for (int c = lo - ch0; c < hi - ch0; ++c)
+            for (int k = 0; k < 128 / cpp; ++k) acc += tf[(k * cpp + c) * 2];
+          fixsum_add_words(sacc + (((lt & 1) * kStatsGroups + (g_first + gl - out_c0 / cpg)) * 2 + mo) * 2, acc);
         }
       };
 
