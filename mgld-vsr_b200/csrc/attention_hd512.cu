@@ -54,7 +54,8 @@ struct Hd512Params {
   int ldo, out_col0;
 };
 
-__global__ void __launch_bounds__(kHdThreads, 1)
+template <int G>   // slabs per TMA operation / ring slot (4 or 2): compile time, so that the MMA issuer's operand descriptors are
+__global__ void __launch_bounds__(kHdThreads, 1)   // base + constant (the scalar chain of the single issuing thread was the bound)
 attention_hd512_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const Hd512Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -71,10 +72,9 @@ attention_hd512_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const int b = blockIdx.z;
   const int kvb = p.kv_batched ? b : 0;
   const int nblk = (p.nkv + kHdKeys - 1) / kHdKeys;
-  const int G = p.group;                      // slabs per ring slot
-  const int nslots = kHdRingSlabs / G;
-  const uint32_t slot_bytes = G * kHdKSlab;
-  const int k_units = kHdChunks / G, v_units = kHdOutChunks / G;
+  constexpr int nslots = kHdRingSlabs / G;
+  constexpr uint32_t slot_bytes = G * kHdKSlab;
+  constexpr int k_units = kHdChunks / G, v_units = kHdOutChunks / G;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -126,21 +126,31 @@ attention_hd512_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       int s = 0;
       uint32_t ph = 0;
       const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      // Descriptors differ only in their 14-bit (address >> 4) field (shared memory < 256 KB: no carry out of it): Q slabs
+      // are base + compile-time offset, the ring slot's base is carried incrementally.
+      const uint64_t dq0 = umma_smem_desc(sQ, 0, 1024, kSwz128);
+      const uint64_t dring0 = umma_smem_desc(sRing, 0, 1024, kSwz128);
+      uint64_t dslot = dring0;
+      uint32_t bar_full = full0, bar_empty = empty0;
+      auto advance = [&]() {
+        dslot += slot_bytes >> 4; bar_full += 8; bar_empty += 8;
+        if (++s == nslots) { s = 0; ph ^= 1; dslot = dring0; bar_full = full0; bar_empty = empty0; }
+      };
       auto issue_s = [&](int j) {
         const uint32_t scol = tmem_base + kHdSCol + (j & 1) * kHdKeys;
+#pragma unroll
         for (int u = 0; u < k_units; ++u) {
-          mbar_wait(full0 + 8 * s, ph);
+          mbar_wait(bar_full, ph);
           tc_fence_after();
-          const uint32_t slot = sRing + s * slot_bytes;
+#pragma unroll
           for (int g = 0; g < G; ++g) {
-            const int c = u * G + g;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_ss(scol, umma_smem_desc(sQ + c * kHdQSlab + k * 32, 0, 1024, kSwz128),
-                      umma_smem_desc(slot + g * kHdKSlab + k * 32, 0, 1024, kSwz128), idesc_s, (c | k) != 0);
+              umma_ss(scol, dq0 + (((u * G + g) * kHdQSlab + k * 32) >> 4), dslot + ((g * kHdKSlab + k * 32) >> 4), idesc_s,
+                      (u | g | k) != 0);
           }
-          umma_commit(empty0 + 8 * s);
-          if (++s == nslots) { s = 0; ph ^= 1; }
+          umma_commit(bar_empty);
+          advance();
         }
         umma_commit(smem_u32(&s_full[j & 1]));
       };
@@ -148,19 +158,20 @@ attention_hd512_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         mbar_wait(smem_u32(&p_full[j & 1]), (j >> 1) & 1);
         tc_fence_after();
         const uint32_t pcol = tmem_base + kHdPCol + (j & 1) * (kHdKeys / 2);
+        const uint32_t acc = j != 0;
+#pragma unroll
         for (int u = 0; u < v_units; ++u) {
-          mbar_wait(full0 + 8 * s, ph);
+          mbar_wait(bar_full, ph);
           tc_fence_after();
-          const uint32_t slot = sRing + s * slot_bytes;
-          for (int g = 0; g < G; ++g) {
-            const int vs = u * G + g;   // 64-column slab of this CTA's output half
+#pragma unroll
+          for (int g = 0; g < G; ++g) {   // 64-column slab u * G + g of this CTA's output half
 #pragma unroll
             for (int k = 0; k < 4; ++k)   // A: 16 keys = 8 packed TMEM columns per step; B: 16 key rows = 2048 B
-              umma_ts(tmem_base + kHdOCol + vs * 64, pcol + k * 8,
-                      umma_smem_desc(slot + g * kHdKSlab + k * 2048, 0, 1024, kSwz128), idesc_o, (j | k) != 0);
+              umma_ts(tmem_base + kHdOCol + (u * G + g) * 64, pcol + k * 8, dslot + ((g * kHdKSlab + k * 2048) >> 4), idesc_o,
+                      k != 0 ? 1u : acc);
           }
-          umma_commit(empty0 + 8 * s);
-          if (++s == nslots) { s = 0; ph ^= 1; }
+          umma_commit(bar_empty);
+          advance();
         }
         umma_commit(smem_u32(&pv_done));
       };
@@ -301,7 +312,8 @@ int launch_attention_hd512(const mgld_attention_desc* d, cudaStream_t stream) {
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    MGLD_CUDA(cudaFuncSetAttribute(attention_hd512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHdSmem));
+    MGLD_CUDA(cudaFuncSetAttribute(attention_hd512_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHdSmem));
+    MGLD_CUDA(cudaFuncSetAttribute(attention_hd512_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHdSmem));
     attr_set = true;
   }
   for (int h = 0; h < d->heads; ++h) {
@@ -315,7 +327,8 @@ int launch_attention_hd512(const mgld_attention_desc* d, cudaStream_t stream) {
     p.scale_log2e = d->scale * 1.4426950408889634f;
     p.out = reinterpret_cast<__half*>(d->out); p.ldo = d->ldo; p.out_col0 = h * kHdDim;
     dim3 grid(ceil_div(d->nq, 128), kHdDim / kHdOutCols, d->batch);
-    MGLD_CUDA(launch_pdl(attention_hd512_kernel, grid, dim3(kHdThreads), (size_t)kHdSmem, stream, tmQ, tmK, tmV, p));
+    MGLD_CUDA(launch_pdl(group == 4 ? attention_hd512_kernel<4> : attention_hd512_kernel<2>, grid, dim3(kHdThreads),
+                         (size_t)kHdSmem, stream, tmQ, tmK, tmV, p));
     MGLD_LAUNCH_CHECK("attention_hd512_kernel");
   }
   return MGLD_OK;
