@@ -6,9 +6,10 @@ plain functional PyTorch (fp32, NCHW, standard ``torch.nn.functional`` ops), dri
 ``state_dict`` — every function cites the reference file:line it follows (paths relative to the reference root).
 
 Pinning: the reference has no golden vectors or tests on this path.  The restatement is pinned against
-the reference's *own modules* imported from /root/reference through ``oracle/ref_shim.py`` (tests/test_oracle_vs_
-reference.py, CPU, run in the build container) and against the fixtures in ``tests/golden/`` that were generated
-from those modules by ``tools/make_golden.py``.
+the reference's *own modules* imported from /root/reference through ``oracle/ref_shim.py`` (tests/test_oracle.py and,
+for the sampler and the script's segment loop, tests/test_reference_pipeline.py; CPU, marker ``reference``, run in the
+build container) and against the fixtures in ``tests/golden/`` that were generated from those modules by
+``tools/make_golden.py``.
 """
 import math
 
