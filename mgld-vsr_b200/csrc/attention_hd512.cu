@@ -11,7 +11,7 @@
 // Both CTAs of a query tile compute the full S = Q K^T (1.5x the algorithmic tensor work) - the price of not exchanging
 // scores between SMs.  Per 64-key block the CTA moves 64 KB of K + 32 KB of V from L2 for 1536 tensor cycles with about
 // 64 KB in flight; measured 2690 cycles per block (655 us per 14400-token frame, 649 TFLOP/s algorithmic; ncu: tensor pipe
-// 47 %, L2 throughput 14 %, DRAM 19 MB against 59 MB of Q + K + V + O - the inputs are L2-resident).  It replaces GEMM ->
+// 61 %, L2 throughput 19 %, DRAM 19 MB against 59 MB of Q + K + V + O - the inputs are L2-resident).  It replaces GEMM ->
 // fp32 scores -> row softmax -> GEMM: 1.9 - 4.2 GB of DRAM traffic per frame and 2.2x the time of the whole block.
 //
 // Roles (192 threads): warp 0 = TMA producer (one elected thread), warp 1 = tcgen05.mma issuer, warps 2-5 = softmax,
